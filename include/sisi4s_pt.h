@@ -1,0 +1,126 @@
+/* sisi4s_pt.h -- C ABI of the B200-native closed-shell CCSD(T) perturbative
+ * triples step (libsisi4s_pt.so).
+ *
+ * This is the drop-in boundary for ONE step of alejandrogallo/sisi4s: the
+ * algorithm `CcsdPerturbativeTriples`
+ *   (reference src/algorithms/CcsdPerturbativeTriples.cxx:119-248, YAML contract
+ *    integration-tests/bench/todo/CcsdPerturbativeTriples/in.yaml)
+ * and its PPPH-integral spelling `PerturbativeTriples`
+ *   (reference src/algorithms/PerturbativeTriples.cxx:172-239, YAML contract
+ *    integration-tests/bench/todo/PerturbativeTriples/in.yaml).
+ * A sisi4s `Algorithm` subclass gathers the CTF tensors once with
+ * `Tensor::read_all` and hands the dense buffers to these entry points
+ * (sisi4s_b200/csrc/CcsdPerturbativeTriplesGpu.cxx).
+ *
+ * Conventions
+ *  - every array is IEEE FP64, dense, COLUMN-MAJOR in the reference's CTF index
+ *    order (first index fastest; docs/manual.org:320), caller-owned host memory;
+ *  - o = number of holes (HoleEigenEnergies->lens[0]), v = number of particles;
+ *  - functions return PT_OK (0) or a negative PtStatus; pt_last_error() gives a
+ *    message for the calling thread.  No C++ types or exceptions cross the ABI;
+ *  - one handle per host thread / GPU.  The library owns all device memory;
+ *  - there is no CPU fallback: without a CUDA device pt_create fails.
+ */
+#ifndef SISI4S_PT_H
+#define SISI4S_PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct PtHandle_ *pt_handle_t;
+
+typedef enum PtStatus {
+  PT_OK = 0,
+  PT_ERR_INVALID = -1,   /* bad argument / call order                          */
+  PT_ERR_CUDA = -2,      /* CUDA runtime error (message in pt_last_error)      */
+  PT_ERR_MISSING = -3,   /* an input tensor was not set before pt_run          */
+  PT_ERR_NOMEM = -4,     /* device memory exhausted                            */
+  PT_ERR_UNSUPPORTED = -5
+} PtStatus;
+
+/* which device implementation pt_run uses */
+typedef enum PtEngine {
+  PT_ENGINE_FUSED = 0,   /* product path: DMMA tiles + on-chip symmetrise/divide/reduce */
+  PT_ENGINE_NAIVE = 1    /* literal on-device restatement (validation only; needs keep_raw) */
+} PtEngine;
+
+typedef struct PtStats {
+  double seconds_run;        /* device time of the last pt_run (CUDA events; incl. list copies) */
+  double seconds_kernel;     /* device time of the triples kernel(s) alone in the last pt_run   */
+  double seconds_upload;     /* host->device copies + packing since pt_create          */
+  double flops_algorithmic;  /* 2 o^3 v^3 (v+o) scaled to the triples of the last run */
+  double bytes_h2d;          /* host->device bytes since pt_create                     */
+  double bytes_d2h;          /* device->host bytes since pt_create                     */
+  double device_bytes;       /* device memory currently held by the handle             */
+  int64_t kernel_launches;   /* kernels launched by this handle since pt_create        */
+  int64_t triples_run;       /* sorted triples processed by the last pt_run            */
+  int32_t sm_count;
+  int32_t reserved;
+} PtStats;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* o, v: dimensions; device: CUDA ordinal.  Replaces the constructor +
+ * sliceTensors() of the reference class (CcsdPerturbativeTriples.cxx:16-79).  */
+int pt_create(pt_handle_t *out, int o, int v, int device);
+int pt_destroy(pt_handle_t h);
+const char *pt_last_error(void);
+const char *pt_version(void);
+
+/* options: "engine" (PtEngine), "keep_raw" (0/1: keep unpacked copies on the
+ * device, required by PT_ENGINE_NAIVE and the debug entry points; set BEFORE
+ * the tensors), "grid" (CTAs of the fused kernel, 0 = one per SM).          */
+int pt_set_option(pt_handle_t h, const char *key, int64_t value);
+
+/* ---- inputs (names = the reference's YAML argument keys) ------------------ */
+/* HoleEigenEnergies[o], ParticleEigenEnergies[v]
+ * (getEnergyDenominator, CcsdPerturbativeTriples.cxx:98-117)                  */
+int pt_set_eigenenergies(pt_handle_t h, const double *epsi, const double *epsa);
+/* CcsdSinglesAmplitudes[v,o]  ("ai", ClusterSinglesDoublesAlgorithm.cxx:42-45) */
+int pt_set_singles(pt_handle_t h, const double *t1);
+/* CcsdDoublesAmplitudes[v,v,o,o] ("abij")                                     */
+int pt_set_doubles(pt_handle_t h, const double *t2);
+/* PPHHCoulombIntegrals[v,v,o,o] (getSinglesContribution, :81-85)              */
+int pt_set_pphh(pt_handle_t h, const double *vabij);
+/* HHHPCoulombIntegrals[o,o,o,v] (hole term of getDoublesContribution, :94)    */
+int pt_set_hhhp(pt_handle_t h, const double *vijka);
+/* PPPHCoulombIntegrals[v,v,v,o] slabs [:,:,:,k0:k1) -- `slab` points at the
+ * first element of slab k0 (v^3 doubles per slab).  May be called repeatedly
+ * with disjoint ranges so the caller never holds more than a few slabs
+ * (PerturbativeTriples.cxx:176,190).                                          */
+int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double *slab);
+/* Alternative to pt_set_ppph_slabs: CoulombVertex Gamma[NF,Np,Np] complex,
+ * given as separate real and imaginary parts (fromComplexTensor,
+ * CcsdPerturbativeTriples.cxx:48-78).  PPPH is built on the device exactly as
+ * CoulombIntegralsFromVertex.cxx:430-431; particles are the last v states.   */
+int pt_set_vertex(pt_handle_t h, int nf, int np, const double *gamma_re, const double *gamma_im);
+
+/* ---- run ------------------------------------------------------------------ */
+/* number of sorted hole triples i<=j<=k = o(o+1)(o+2)/6, enumerated in the
+ * reference's loop order (CcsdPerturbativeTriples.cxx:156-158)                */
+int64_t pt_num_triples(int o);
+/* contiguous share [begin,end) of the sorted-triple enumeration for `rank` of
+ * `nranks`, balanced by the number of distinct hole permutations (6/3/3/1)    */
+int pt_partition(int o, int nranks, int rank, int64_t *begin, int64_t *end);
+/* Computes sum_{t in [begin,end)} E_t, the (T) energy contribution of those
+ * sorted triples (the body of the reference loop, :159-216).  e_triples: the
+ * sum; e_per_triple: NULL or end-begin doubles.  The caller adds CcsdEnergy
+ * (:241-247) and, across GPUs, all-reduces the scalar.                        */
+int pt_run(pt_handle_t h, int64_t begin, int64_t end, double *e_triples, double *e_per_triple);
+int pt_get_stats(pt_handle_t h, PtStats *stats);
+
+/* ---- debug / measurement helpers (not part of the drop-in contract) ------- */
+/* one 16x16x16 tile of W_{xyz}[a,b,c] (getDoublesContribution) computed by the
+ * fused kernel's own main loop; out[la + 16*(lb + 16*lc)]                     */
+int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, double *out);
+/* FP64 issue-rate microbenchmarks on the handle's device: mode 0 = DMMA.8x8x4,
+ * mode 1 = DFMA.  Returns achieved TFLOP/s over `iters` inner iterations.     */
+int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double *tflops, double *sm_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SISI4S_PT_H */

@@ -1,0 +1,534 @@
+// pt_api.cu -- extern "C" layer of libsisi4s_pt (see include/sisi4s_pt.h).
+// Host logic only: handle lifetime, uploads + one-time packing, the triple /
+// orbit work lists, launches, and the final fixed-order summation.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pt_common.cuh"
+
+using namespace pt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(e_ == cudaErrorMemoryAllocation ? PT_ERR_NOMEM : PT_ERR_CUDA,          \
+                  "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+  } while (0)
+
+}  // namespace
+
+struct PtHandle_ {
+  Dims d{};
+  int device = 0;
+  int sm_count = 0;
+  int engine = PT_ENGINE_FUSED;
+  int keep_raw = 0;
+  int grid = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // raw device tensors
+  double *epsi = nullptr, *epsa = nullptr, *t1 = nullptr, *pphh = nullptr;
+  double *t2_raw = nullptr, *hhhp_raw = nullptr, *ppph_raw = nullptr;  // keep_raw only
+  // packed
+  double *Tt = nullptr, *T2h = nullptr, *Vt = nullptr, *Ut = nullptr;
+  double* slab_stage = nullptr;  // one raw PPPH slab
+  std::vector<char> slab_set;
+  bool have_eps = false, have_t1 = false, have_t2 = false, have_pphh = false, have_hhhp = false;
+  // work lists
+  uchar4* d_orbits = nullptr;
+  int norbits = 0;
+  PtStats stats{};
+  double bytes_alloc = 0;
+
+  template <typename T>
+  cudaError_t alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e == cudaSuccess) bytes_alloc += (double)(n * sizeof(T));
+    return e;
+  }
+};
+
+namespace {
+
+struct Triple { int i, j, k; };
+
+// reference enumeration order, CcsdPerturbativeTriples.cxx:156-158
+void enumerate_triples(int o, std::vector<Triple>& out) {
+  out.clear();
+  for (int i = 0; i < o; ++i)
+    for (int j = i; j < o; ++j)
+      for (int k = j; k < o; ++k) out.push_back({i, j, k});
+}
+inline int triple_class(const Triple& t) { return (t.i == t.j ? 1 : 0) + (t.j == t.k ? 2 : 0); }
+inline int triple_weight(const Triple& t) {
+  static const int w[4] = {6, 3, 3, 1};
+  return w[triple_class(t)];
+}
+
+struct Timer {
+  cudaEvent_t a, b;
+  cudaStream_t s;
+  Timer(cudaEvent_t a_, cudaEvent_t b_, cudaStream_t s_) : a(a_), b(b_), s(s_) { cudaEventRecord(a, s); }
+  double stop() {
+    cudaEventRecord(b, s);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms * 1e-3;
+  }
+};
+
+int upload(pt_handle_t h, double* dst, const double* src, size_t n) {
+  CU(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->stats.bytes_h2d += (double)(n * sizeof(double));
+  return PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pt_last_error(void) { return g_last_error.c_str(); }
+const char* pt_version(void) { return "sisi4s_b200 (T) 0.1 sm_100a"; }
+
+int64_t pt_num_triples(int o) { return (int64_t)o * (o + 1) * (o + 2) / 6; }
+
+int pt_partition(int o, int nranks, int rank, int64_t* begin, int64_t* end) {
+  if (o < 1 || nranks < 1 || rank < 0 || rank >= nranks || !begin || !end)
+    return fail(PT_ERR_INVALID, "pt_partition: bad arguments");
+  std::vector<Triple> tr;
+  enumerate_triples(o, tr);
+  // contiguous chunks of (nearly) equal weight = number of W blocks to build
+  long long total = 0;
+  for (auto& t : tr) total += triple_weight(t);
+  auto cut = [&](int r) -> int64_t {
+    if (r <= 0) return 0;
+    if (r >= nranks) return (int64_t)tr.size();
+    const double target = (double)total * r / nranks;
+    long long acc = 0;
+    for (size_t n = 0; n < tr.size(); ++n) {
+      if ((double)acc >= target) return (int64_t)n;
+      acc += triple_weight(tr[n]);
+    }
+    return (int64_t)tr.size();
+  };
+  *begin = cut(rank);
+  *end = cut(rank + 1);
+  return PT_OK;
+}
+
+int pt_create(pt_handle_t* out, int o, int v, int device) {
+  if (!out || o < 1 || v < 1) return fail(PT_ERR_INVALID, "pt_create: need o>=1, v>=1");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PT_ERR_CUDA, "pt_create: no CUDA device (%s); this library has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(PT_ERR_INVALID, "pt_create: device %d of %d", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(PT_ERR_UNSUPPORTED, "pt_create: device sm_%d%d, built for sm_100a only", prop.major,
+                prop.minor);
+  pt_handle_t h = new PtHandle_();
+  h->d = make_dims(o, v);
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->stats.sm_count = prop.multiProcessorCount;
+  h->slab_set.assign(o, 0);
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(fused_configure(nullptr));
+  // orbit list: A >= B >= C, C fastest
+  std::vector<uchar4> orb;
+  for (int A = 0; A < h->d.nr; ++A)
+    for (int B = 0; B <= A; ++B)
+      for (int C = 0; C <= B; ++C) {
+        uchar4 u;
+        u.x = (unsigned char)A; u.y = (unsigned char)B; u.z = (unsigned char)C;
+        u.w = (unsigned char)((A == B ? 1 : 0) + (B == C ? 2 : 0));
+        orb.push_back(u);
+      }
+  if (h->d.nr > 255) return fail(PT_ERR_UNSUPPORTED, "pt_create: v too large (nr=%d > 255)", h->d.nr);
+  h->norbits = (int)orb.size();
+  CU(h->alloc(&h->d_orbits, orb.size()));
+  CU(cudaMemcpy(h->d_orbits, orb.data(), orb.size() * sizeof(uchar4), cudaMemcpyHostToDevice));
+  *out = h;
+  return PT_OK;
+}
+
+int pt_destroy(pt_handle_t h) {
+  if (!h) return PT_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  double* ptrs[] = {h->epsi, h->epsa, h->t1, h->pphh, h->t2_raw, h->hhhp_raw, h->ppph_raw,
+                    h->Tt, h->T2h, h->Vt, h->Ut, h->slab_stage};
+  for (double* p : ptrs)
+    if (p) cudaFree(p);
+  if (h->d_orbits) cudaFree(h->d_orbits);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return PT_OK;
+}
+
+int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
+  if (!h || !key) return fail(PT_ERR_INVALID, "pt_set_option: null");
+  if (!strcmp(key, "engine")) {
+    if (value != PT_ENGINE_FUSED && value != PT_ENGINE_NAIVE) return fail(PT_ERR_INVALID, "engine %lld", (long long)value);
+    h->engine = (int)value;
+  } else if (!strcmp(key, "keep_raw")) {
+    h->keep_raw = value != 0;
+  } else if (!strcmp(key, "grid")) {
+    if (value < 0) return fail(PT_ERR_INVALID, "grid %lld", (long long)value);
+    h->grid = (int)value;
+  } else {
+    return fail(PT_ERR_INVALID, "pt_set_option: unknown key '%s'", key);
+  }
+  return PT_OK;
+}
+
+int pt_set_eigenenergies(pt_handle_t h, const double* epsi, const double* epsa) {
+  if (!h || !epsi || !epsa) return fail(PT_ERR_INVALID, "pt_set_eigenenergies: null");
+  CU(cudaSetDevice(h->device));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  if (!h->epsi) CU(h->alloc(&h->epsi, h->d.o));
+  if (!h->epsa) CU(h->alloc(&h->epsa, h->d.v));
+  if (int rc = upload(h, h->epsi, epsi, h->d.o)) return rc;
+  if (int rc = upload(h, h->epsa, epsa, h->d.v)) return rc;
+  h->stats.seconds_upload += tm.stop();
+  h->have_eps = true;
+  return PT_OK;
+}
+
+int pt_set_singles(pt_handle_t h, const double* t1) {
+  if (!h || !t1) return fail(PT_ERR_INVALID, "pt_set_singles: null");
+  CU(cudaSetDevice(h->device));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t n = (size_t)h->d.v * h->d.o;
+  if (!h->t1) CU(h->alloc(&h->t1, n));
+  if (int rc = upload(h, h->t1, t1, n)) return rc;
+  h->stats.seconds_upload += tm.stop();
+  h->have_t1 = true;
+  return PT_OK;
+}
+
+int pt_set_pphh(pt_handle_t h, const double* vabij) {
+  if (!h || !vabij) return fail(PT_ERR_INVALID, "pt_set_pphh: null");
+  CU(cudaSetDevice(h->device));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t n = (size_t)h->d.v * h->d.v * h->d.o * h->d.o;
+  if (!h->pphh) CU(h->alloc(&h->pphh, n));
+  if (int rc = upload(h, h->pphh, vabij, n)) return rc;
+  h->stats.seconds_upload += tm.stop();
+  h->have_pphh = true;
+  return PT_OK;
+}
+
+int pt_set_doubles(pt_handle_t h, const double* t2) {
+  if (!h || !t2) return fail(PT_ERR_INVALID, "pt_set_doubles: null");
+  CU(cudaSetDevice(h->device));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t n = (size_t)h->d.v * h->d.v * h->d.o * h->d.o;
+  double* raw = h->t2_raw;
+  if (!raw) {
+    CU(cudaMalloc((void**)&raw, n * sizeof(double)));
+    if (h->keep_raw) { h->t2_raw = raw; h->bytes_alloc += (double)(n * sizeof(double)); }
+  }
+  if (int rc = upload(h, raw, t2, n)) return rc;
+  if (!h->Tt) CU(h->alloc(&h->Tt, tt_elems(h->d)));
+  if (!h->T2h) CU(h->alloc(&h->T2h, t2h_elems(h->d)));
+  CU(launch_pack_tt(raw, h->Tt, h->d, h->stream));
+  CU(launch_pack_t2h(raw, h->T2h, h->d, h->stream));
+  h->stats.kernel_launches += 2;
+  h->stats.seconds_upload += tm.stop();
+  if (!h->keep_raw) CU(cudaFree(raw));
+  h->have_t2 = true;
+  return PT_OK;
+}
+
+int pt_set_hhhp(pt_handle_t h, const double* vijka) {
+  if (!h || !vijka) return fail(PT_ERR_INVALID, "pt_set_hhhp: null");
+  CU(cudaSetDevice(h->device));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t n = (size_t)h->d.o * h->d.o * h->d.o * h->d.v;
+  double* raw = h->hhhp_raw;
+  if (!raw) {
+    CU(cudaMalloc((void**)&raw, n * sizeof(double)));
+    if (h->keep_raw) { h->hhhp_raw = raw; h->bytes_alloc += (double)(n * sizeof(double)); }
+  }
+  if (int rc = upload(h, raw, vijka, n)) return rc;
+  if (!h->Ut) CU(h->alloc(&h->Ut, ut_elems(h->d)));
+  CU(launch_pack_ut(raw, h->Ut, h->d, h->stream));
+  h->stats.kernel_launches += 1;
+  h->stats.seconds_upload += tm.stop();
+  if (!h->keep_raw) CU(cudaFree(raw));
+  h->have_hhhp = true;
+  return PT_OK;
+}
+
+static int ensure_ppph_buffers(pt_handle_t h) {
+  const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+  if (!h->Vt) CU(h->alloc(&h->Vt, vt_elems(h->d)));
+  if (!h->slab_stage) CU(h->alloc(&h->slab_stage, slab));
+  if (h->keep_raw && !h->ppph_raw) CU(h->alloc(&h->ppph_raw, slab * h->d.o));
+  return PT_OK;
+}
+
+int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
+  if (!h || !slabs) return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: null");
+  if (k0 < 0 || k1 > h->d.o || k0 >= k1) return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: range [%d,%d) of %d", k0, k1, h->d.o);
+  CU(cudaSetDevice(h->device));
+  if (int rc = ensure_ppph_buffers(h)) return rc;
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+  for (int k = k0; k < k1; ++k) {
+    double* dst = h->keep_raw ? h->ppph_raw + slab * k : h->slab_stage;
+    if (int rc = upload(h, dst, slabs + slab * (size_t)(k - k0), slab)) return rc;
+    CU(launch_pack_vt_slab(dst, h->Vt + vt_slab_elems(h->d) * k, h->d, h->stream));
+    h->stats.kernel_launches += 1;
+    h->slab_set[k] = 1;
+  }
+  h->stats.seconds_upload += tm.stop();
+  return PT_OK;
+}
+
+int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double* gim) {
+  if (!h || !gre || !gim) return fail(PT_ERR_INVALID, "pt_set_vertex: null");
+  if (nf < 1 || np < h->d.o + h->d.v) return fail(PT_ERR_INVALID, "pt_set_vertex: nf=%d np=%d (o+v=%d)", nf, np, h->d.o + h->d.v);
+  CU(cudaSetDevice(h->device));
+  if (int rc = ensure_ppph_buffers(h)) return rc;
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t n = (size_t)nf * np * np, slab = (size_t)h->d.v * h->d.v * h->d.v;
+  double *dre = nullptr, *dim_ = nullptr;
+  CU(cudaMalloc((void**)&dre, n * sizeof(double)));
+  CU(cudaMalloc((void**)&dim_, n * sizeof(double)));
+  if (int rc = upload(h, dre, gre, n)) return rc;
+  if (int rc = upload(h, dim_, gim, n)) return rc;
+  for (int k = 0; k < h->d.o; ++k) {
+    double* dst = h->keep_raw ? h->ppph_raw + slab * k : h->slab_stage;
+    CU(launch_ppph_slab_from_vertex(dre, dim_, nf, np, k, dst, h->d, h->stream));
+    CU(launch_pack_vt_slab(dst, h->Vt + vt_slab_elems(h->d) * k, h->d, h->stream));
+    h->stats.kernel_launches += 2;
+    h->slab_set[k] = 1;
+  }
+  h->stats.seconds_upload += tm.stop();
+  CU(cudaFree(dre));
+  CU(cudaFree(dim_));
+  return PT_OK;
+}
+
+static int check_inputs(pt_handle_t h) {
+  if (!h->have_eps) return fail(PT_ERR_MISSING, "Missing argument: HoleEigenEnergies/ParticleEigenEnergies");
+  if (!h->have_t1) return fail(PT_ERR_MISSING, "Missing argument: CcsdSinglesAmplitudes");
+  if (!h->have_t2) return fail(PT_ERR_MISSING, "Missing argument: CcsdDoublesAmplitudes");
+  if (!h->have_pphh) return fail(PT_ERR_MISSING, "Missing argument: PPHHCoulombIntegrals");
+  if (!h->have_hhhp) return fail(PT_ERR_MISSING, "Missing argument: HHHPCoulombIntegrals");
+  for (int k = 0; k < h->d.o; ++k)
+    if (!h->slab_set[k]) return fail(PT_ERR_MISSING, "Missing argument: PPPHCoulombIntegrals slab %d (or CoulombVertex)", k);
+  return PT_OK;
+}
+
+static FusedParams make_params(pt_handle_t h) {
+  FusedParams p{};
+  p.d = h->d;
+  p.Tt = h->Tt; p.T2h = h->T2h; p.Vt = h->Vt; p.Ut = h->Ut;
+  p.t1 = h->t1; p.pphh = h->pphh; p.epsi = h->epsi; p.epsa = h->epsa;
+  p.orbits = h->d_orbits;
+  p.norbits = h->norbits;
+  return p;
+}
+
+static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<double>& e_out) {
+  if (!h->t2_raw || !h->ppph_raw || !h->hhhp_raw)
+    return fail(PT_ERR_INVALID, "PT_ENGINE_NAIVE needs option keep_raw=1 set before the tensors");
+  const size_t n3 = (size_t)h->d.v * h->d.v * h->d.v;
+  double* w = nullptr;
+  double* d_e = nullptr;
+  CU(cudaMalloc((void**)&w, 6 * n3 * sizeof(double)));
+  CU(cudaMalloc((void**)&d_e, tr.size() * sizeof(double)));
+  CU(cudaMemsetAsync(d_e, 0, tr.size() * sizeof(double), h->stream));
+  static const int perm[6][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}};
+  for (size_t n = 0; n < tr.size(); ++n) {
+    const int hh[3] = {tr[n].i, tr[n].j, tr[n].k};
+    const double* w6[6];
+    int hp[6][3];
+    for (int p = 0; p < 6; ++p) {
+      for (int m = 0; m < 3; ++m) hp[p][m] = hh[perm[p][m]];
+      int q = 0;
+      for (; q < p; ++q)
+        if (hp[q][0] == hp[p][0] && hp[q][1] == hp[p][1] && hp[q][2] == hp[p][2]) break;
+      w6[p] = w + n3 * p;
+      if (q == p) {
+        CU(launch_naive_w(h->t2_raw, h->ppph_raw, h->hhhp_raw, h->d, hp[p][0], hp[p][1], hp[p][2],
+                          w + n3 * p, h->stream));
+        h->stats.kernel_launches += 1;
+      }
+    }
+    CU(launch_naive_energy(w6, h->t1, h->pphh, h->epsi, h->epsa, h->d, hh[0], hh[1], hh[2], d_e + n,
+                           h->stream));
+    h->stats.kernel_launches += 1;
+  }
+  e_out.resize(tr.size());
+  CU(cudaMemcpyAsync(e_out.data(), d_e, tr.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->stats.bytes_d2h += (double)(tr.size() * sizeof(double));
+  CU(cudaFree(w));
+  CU(cudaFree(d_e));
+  return PT_OK;
+}
+
+int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double* e_per_triple) {
+  if (!h || !e_triples) return fail(PT_ERR_INVALID, "pt_run: null");
+  CU(cudaSetDevice(h->device));
+  if (int rc = check_inputs(h)) return rc;
+  std::vector<Triple> all;
+  enumerate_triples(h->d.o, all);
+  if (begin < 0 || end > (int64_t)all.size() || begin > end)
+    return fail(PT_ERR_INVALID, "pt_run: triple range [%lld,%lld) of %zu", (long long)begin, (long long)end, all.size());
+  std::vector<Triple> tr(all.begin() + begin, all.begin() + end);
+  std::vector<double> e(tr.size(), 0.0);
+  Timer tm(h->ev0, h->ev1, h->stream);
+  long long weight = 0;
+  for (auto& t : tr) weight += triple_weight(t);
+
+  if (h->engine == PT_ENGINE_NAIVE) {
+    if (int rc = run_naive(h, tr, e)) return rc;
+  } else {
+    // i=j=k triples contribute exactly zero (sum of the spin factors over S3 vanishes), the
+    // reference only accumulates rounding noise there (CcsdPerturbativeTriples.cxx:156-158)
+    std::vector<int4> list;
+    std::vector<int> where;
+    for (size_t n = 0; n < tr.size(); ++n) {
+      const int c = triple_class(tr[n]);
+      if (c == 3) continue;
+      list.push_back(make_int4(tr[n].i, tr[n].j, tr[n].k, c));
+      where.push_back((int)n);
+    }
+    if (!list.empty()) {
+      int4* d_list = nullptr;
+      double* d_e = nullptr;
+      CU(cudaMalloc((void**)&d_list, list.size() * sizeof(int4)));
+      CU(cudaMalloc((void**)&d_e, list.size() * sizeof(double)));
+      CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemsetAsync(d_e, 0, list.size() * sizeof(double), h->stream));
+      FusedParams p = make_params(h);
+      p.triples = d_list;
+      p.nitems = (long long)list.size() * h->norbits;
+      p.e_triple = d_e;
+      int grid = h->grid > 0 ? h->grid : h->sm_count;
+      if ((long long)grid > p.nitems) grid = (int)p.nitems;
+      cudaEvent_t k0, k1;
+      CU(cudaEventCreate(&k0));
+      CU(cudaEventCreate(&k1));
+      CU(cudaEventRecord(k0, h->stream));
+      CU(launch_fused(p, grid, h->stream));
+      CU(cudaEventRecord(k1, h->stream));
+      CU(cudaEventSynchronize(k1));
+      float kms = 0;
+      CU(cudaEventElapsedTime(&kms, k0, k1));
+      h->stats.seconds_kernel = kms * 1e-3;
+      CU(cudaEventDestroy(k0));
+      CU(cudaEventDestroy(k1));
+      h->stats.kernel_launches += 1;
+      std::vector<double> el(list.size());
+      CU(cudaMemcpyAsync(el.data(), d_e, list.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      h->stats.bytes_h2d += (double)(list.size() * sizeof(int4));
+      h->stats.bytes_d2h += (double)(list.size() * sizeof(double));
+      for (size_t n = 0; n < list.size(); ++n) e[where[n]] = el[n];
+      CU(cudaFree(d_list));
+      CU(cudaFree(d_e));
+    }
+  }
+  h->stats.seconds_run = tm.stop();
+  if (h->engine == PT_ENGINE_NAIVE) h->stats.seconds_kernel = h->stats.seconds_run;
+  // fixed-order summation in extended precision
+  long double sum = 0.0L;
+  for (double x : e) sum += (long double)x;
+  *e_triples = (double)sum;
+  if (e_per_triple) std::copy(e.begin(), e.end(), e_per_triple);
+  const double o = h->d.o, v = h->d.v;
+  h->stats.flops_algorithmic = 2.0 * v * v * v * (v + o) * (double)weight;
+  h->stats.triples_run = (int64_t)tr.size();
+  return PT_OK;
+}
+
+int pt_get_stats(pt_handle_t h, PtStats* s) {
+  if (!h || !s) return fail(PT_ERR_INVALID, "pt_get_stats: null");
+  h->stats.device_bytes = h->bytes_alloc;
+  *s = h->stats;
+  return PT_OK;
+}
+
+int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, double* out) {
+  if (!h || !out) return fail(PT_ERR_INVALID, "pt_debug_w_tile: null");
+  CU(cudaSetDevice(h->device));
+  if (int r = check_inputs(h)) return r;
+  const int o = h->d.o, nr = h->d.nr;
+  if (x < 0 || y < 0 || z < 0 || x >= o || y >= o || z >= o || ra < 0 || rb < 0 || rc < 0 || ra >= nr || rb >= nr || rc >= nr)
+    return fail(PT_ERR_INVALID, "pt_debug_w_tile: index out of range");
+  double* d_out = nullptr;
+  CU(cudaMalloc((void**)&d_out, XT_DBL * sizeof(double)));
+  FusedParams p = make_params(h);
+  WTileJob job{x, y, z, ra, rb, rc};
+  CU(launch_w_tile(p, job, d_out, h->stream));
+  h->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(out, d_out, XT_DBL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaFree(d_out));
+  return PT_OK;
+}
+
+int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double* tflops, double* sm_mhz_est) {
+  if (!h || !tflops) return fail(PT_ERR_INVALID, "pt_bench_fp64: null");
+  if (warps_per_sm < 1 || warps_per_sm > 32 || iters < 1) return fail(PT_ERR_INVALID, "pt_bench_fp64: args");
+  CU(cudaSetDevice(h->device));
+  double* sink = nullptr;
+  unsigned long long* cyc = nullptr;
+  const int blocks = h->sm_count;
+  CU(cudaMalloc((void**)&sink, sizeof(double)));
+  CU(cudaMalloc((void**)&cyc, blocks * sizeof(unsigned long long)));
+  CU(launch_bench_fp64(mode, blocks, warps_per_sm, iters / 8 + 1, sink, cyc, h->stream));  // warm-up
+  CU(cudaStreamSynchronize(h->stream));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  CU(launch_bench_fp64(mode, blocks, warps_per_sm, iters, sink, cyc, h->stream));
+  const double sec = tm.stop();
+  h->stats.kernel_launches += 2;
+  std::vector<unsigned long long> hc(blocks);
+  CU(cudaMemcpy(hc.data(), cyc, blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  unsigned long long mx = 0;
+  for (auto c : hc) mx = std::max(mx, c);
+  // mode 0: 8 DMMA (256 FMA each) per warp per iteration; mode 1: 16 DFMA per thread per iteration
+  const double fma_per_warp_iter = mode == 0 ? 8.0 * 256.0 : 16.0 * 32.0;
+  const double flops = 2.0 * fma_per_warp_iter * (double)iters * warps_per_sm * blocks;
+  *tflops = flops / sec * 1e-12;
+  if (sm_mhz_est) *sm_mhz_est = (double)mx / sec * 1e-6;
+  CU(cudaFree(sink));
+  CU(cudaFree(cyc));
+  return PT_OK;
+}
+
+}  // extern "C"

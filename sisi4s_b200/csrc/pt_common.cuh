@@ -1,0 +1,117 @@
+// pt_common.cuh -- shared definitions of libsisi4s_pt (host + device).
+//
+// Data layout in HBM (all FP64).  "Raw" arrays keep the reference's CTF
+// column-major layouts; "packed" arrays are pre-tiled images of exactly what one
+// pipeline stage of the fused kernel stages in shared memory, so that every
+// stage is a handful of contiguous cp.async.bulk (TMA engine, SASS UBLKCP)
+// copies and every DMMA fragment load is a conflict-free 256-byte warp read.
+//
+//   TILE = 16 particle indices per range, nr = ceil(v/16) ranges, vp = 16 nr
+//   nk4 = ceil(v/4) chunks of the particle contraction index d
+//   nl4 = ceil(o/4) chunks of the hole contraction index l
+//
+//   Vt [z][Q][R][dc][n=256][kk=4]      = Vppph[b=16Q+n/16, c=16R+n%16, d=4dc+kk, z]
+//   Tt [y][x][P][dc][m=16][kk=4]       = T2[a=16P+m, d=4dc+kk, x, y]
+//   T2h[x][P][Q][lc][g=2][b8=8][m=16][kk=4] = T2[a=16P+m, b=16Q+8g+b8, x, l=4lc+kk]
+//   Ut [z][y][R][lc][c=16][kk=4]       = -Vhhhp[y, z, l=4lc+kk, c=16R+c]
+//
+// Out-of-range elements (a,b,c,d >= v or l >= o) are stored as zeros, so the
+// kernels need no boundary handling in the contraction loops.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/sisi4s_pt.h"
+
+namespace pt {
+
+constexpr int TILE = 16;
+constexpr int STAGE_DBL = 1152;            // doubles per pipeline stage (9216 B)
+constexpr int NSTAGE = 3;
+constexpr int XT_DBL = TILE * TILE * TILE; // one X tile
+constexpr int NCONSUMER_WARPS = 8;
+constexpr int FUSED_THREADS = (NCONSUMER_WARPS + 1) * 32;
+
+struct Dims {
+  int o, v;
+  int nr;    // particle ranges
+  int vp;    // 16*nr
+  int nk4;   // ceil(v/4)
+  int nl4;   // ceil(o/4)
+};
+
+__host__ __device__ inline Dims make_dims(int o, int v) {
+  Dims d;
+  d.o = o; d.v = v;
+  d.nr = (v + TILE - 1) / TILE;
+  d.vp = d.nr * TILE;
+  d.nk4 = (v + 3) / 4;
+  d.nl4 = (o + 3) / 4;
+  return d;
+}
+
+__host__ __device__ inline size_t vt_slab_elems(const Dims& d) { return (size_t)d.nr * d.nr * d.nk4 * 1024; }
+__host__ __device__ inline size_t vt_elems(const Dims& d) { return vt_slab_elems(d) * d.o; }
+__host__ __device__ inline size_t tt_elems(const Dims& d) { return (size_t)d.o * d.o * d.nr * d.nk4 * 64; }
+__host__ __device__ inline size_t t2h_elems(const Dims& d) { return (size_t)d.o * d.nr * d.nr * d.nl4 * 1024; }
+__host__ __device__ inline size_t ut_elems(const Dims& d) { return (size_t)d.o * d.o * d.nr * d.nl4 * 64; }
+
+__host__ __device__ inline size_t vt_tile_off(const Dims& d, int z, int Q, int R) {
+  return (((size_t)z * d.nr + Q) * d.nr + R) * d.nk4 * 1024;
+}
+__host__ __device__ inline size_t tt_panel_off(const Dims& d, int x, int y, int P) {
+  return (((size_t)y * d.o + x) * d.nr + P) * d.nk4 * 64;
+}
+__host__ __device__ inline size_t t2h_block_off(const Dims& d, int x, int P, int Q) {
+  return (((size_t)x * d.nr + P) * d.nr + Q) * d.nl4 * 1024;
+}
+__host__ __device__ inline size_t ut_panel_off(const Dims& d, int y, int z, int R) {
+  return (((size_t)z * d.o + y) * d.nr + R) * d.nl4 * 64;
+}
+
+// ---- parameters of the fused kernel ---------------------------------------
+struct FusedParams {
+  Dims d;
+  const double* Tt;
+  const double* T2h;
+  const double* Vt;
+  const double* Ut;
+  const double* t1;    // raw [v,o]
+  const double* pphh;  // raw [v,v,o,o]
+  const double* epsi;
+  const double* epsa;
+  const int4* triples;    // (i,j,k,class) of the sorted triples of this run
+  const uchar4* orbits;   // (A,B,C,class), A>=B>=C
+  int norbits;
+  long long nitems;       // ntriples * norbits
+  double* e_triple;       // [ntriples], accumulated with atomicAdd
+};
+
+// one W tile job of the debug kernel
+struct WTileJob { int x, y, z, P, Q, R; };
+
+// ---- host-side launchers (defined in the .cu files) ------------------------
+cudaError_t launch_pack_vt_slab(const double* raw_slab, double* vt_slab, Dims d, cudaStream_t s);
+cudaError_t launch_pack_tt(const double* t2, double* tt, Dims d, cudaStream_t s);
+cudaError_t launch_pack_t2h(const double* t2, double* t2h, Dims d, cudaStream_t s);
+cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, cudaStream_t s);
+cudaError_t launch_ppph_slab_from_vertex(const double* gre, const double* gim, int nf, int np,
+                                         int z, double* raw_slab, Dims d, cudaStream_t s);
+
+cudaError_t fused_configure(int* smem_bytes_out);
+cudaError_t launch_fused(const FusedParams& p, int grid, cudaStream_t s);
+cudaError_t launch_w_tile(const FusedParams& p, WTileJob job, double* d_out, cudaStream_t s);
+
+cudaError_t launch_naive_w(const double* t2, const double* ppph, const double* hhhp, Dims d,
+                           int x, int y, int z, double* w, cudaStream_t s);
+cudaError_t launch_naive_energy(const double* const* w6, const double* t1, const double* pphh,
+                                const double* epsi, const double* epsa, Dims d, int i, int j, int k,
+                                double* e_out, cudaStream_t s);
+
+cudaError_t launch_bench_fp64(int mode, int blocks, int warps, int iters, double* d_sink,
+                              unsigned long long* d_cycles, cudaStream_t s);
+
+}  // namespace pt

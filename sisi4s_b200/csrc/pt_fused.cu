@@ -1,0 +1,528 @@
+// pt_fused.cu -- the product kernel of the (T) step.
+//
+// One persistent CTA per SM.  A work item is (sorted hole triple i<=j<=k, orbit
+// {A>=B>=C} of 16-wide particle ranges).  For an item the CTA
+//   1. runs the table-driven list of stacked GEMM steps (tools/gen_tables.py):
+//      each step contracts up to two 16-row T2 panels with ONE shared 256-pair
+//      tile of a PPPH slab (K = v) plus the hole term (K = o) on FP64 tensor
+//      cores (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4), operands streamed from the
+//      pre-tiled HBM layouts by cp.async.bulk (TMA engine, SASS UBLKCP) through a
+//      3-stage mbarrier ring filled by a dedicated producer warp;
+//   2. adds each 16^3 W tile, index-permuted, into the orbit's X tiles, which
+//      live in shared memory for the whole item (6 x 32 KB) -- the v^3 triples
+//      blocks are never written to HBM;
+//   3. epilogue: permutational symmetrisation (six index permutations with the
+//      spin factors), singles term, eigenvalue denominator, warp-shuffle
+//      reduction, one atomicAdd per item into the triple's energy.
+//
+// This replaces, per sorted triple, getDoublesContribution / the permutation
+// accumulate / divide / spin-factor symmetrise / energy dot of the reference
+// (src/algorithms/CcsdPerturbativeTriples.cxx:87-96,161-216), i.e. ~150
+// collective CTF operations on v^3 tensors.
+//
+// Fragment conventions (PTX ISA, mma.m8n8k4 .f64):
+//   A (8x4, row):  a  = A[lane>>2][lane&3]
+//   B (4x8, col):  b  = B[lane&3][lane>>2]
+//   C (8x8):       c0,c1 = C[lane>>2][2*(lane&3) + {0,1}]
+// Warp w of the 8 consumer warps owns, of the stacked 32 x (16b x 16c) output,
+// all 4 row fragments (half h = 0,1; mf = 0,1) and the columns
+// b in {w, w+8}, c-octet co in {0,1}:  acc[h][mf][bi][co][e] is
+//   W_h[la = 8 mf + (lane>>2), lb = w + 8 bi, lc = 8 co + 2 (lane&3) + e].
+#include "pt_common.cuh"
+#include "pt_tables.h"
+
+namespace pt {
+
+__constant__ PtClassTable c_tab[4][4] = PT_TABLES_INIT;
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int sel3(int a, int b, int c, int idx) {
+  return idx == 0 ? a : (idx == 1 ? b : c);
+}
+// X-tile element index with the XOR swizzle chosen by tools/swizzle_search.py:
+// low nibble x0 ^ x1 ^ bitswap13(x2); at most 2-way bank conflicts for every
+// permuted accumulate / read pattern of the kernel.
+__device__ __forceinline__ int xt_index(int x0, int x1, int x2) {
+  const int s2 = (x2 & 5) | ((x2 & 2) << 2) | ((x2 & 8) >> 2);
+  return (x0 ^ x1 ^ s2) + 16 * x1 + 256 * x2;
+}
+
+// ------------------------------------------------------------ step descriptors
+struct StepSrc {
+  const double* v;      // Vt tile            (nk4 chunks of 1024)
+  const double* t[2];   // Tt panels          (nk4 chunks of 64)
+  const double* hh[2];  // T2h blocks         (nl4 * 2 chunks of 512)
+  const double* u[2];   // Ut panels          (nl4 chunks of 64)
+  int en[2];
+};
+
+__device__ __forceinline__ StepSrc make_step_src(const FusedParams& p, const PtStep& st, int h0, int h1,
+                                                 int h2, int rg0, int rg1, int rg2) {
+  StepSrc s;
+  const int z = sel3(h0, h1, h2, st.zs);
+  const int P = sel3(rg0, rg1, rg2, st.r0);
+  const int Q = sel3(rg0, rg1, rg2, st.r1);
+  const int R = sel3(rg0, rg1, rg2, st.r2);
+  s.v = p.Vt + vt_tile_off(p.d, z, Q, R);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int x = sel3(h0, h1, h2, st.h[h].tx);
+    const int y = sel3(h0, h1, h2, st.h[h].ty);
+    s.en[h] = st.h[h].en;
+    s.t[h] = p.Tt + tt_panel_off(p.d, x, y, P);
+    s.hh[h] = p.T2h + t2h_block_off(p.d, x, P, Q);
+    s.u[h] = p.Ut + ut_panel_off(p.d, y, z, R);
+  }
+  return s;
+}
+
+struct Pipe {
+  uint32_t ring;   // shared address of stage 0
+  uint32_t full;   // shared address of full[0]
+  uint32_t empty;  // shared address of empty[0]
+  uint32_t slot;
+  uint32_t phase;
+  __device__ __forceinline__ void advance() {
+    if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+  }
+};
+
+// producer side of one step: nk4 particle-contraction stages, then 2*nl4 hole stages
+__device__ __forceinline__ void produce_step(const StepSrc& s, Pipe& pp, int nk4, int nl4) {
+  const uint32_t nen = (uint32_t)(s.en[0] + s.en[1]);
+  for (int dc = 0; dc < nk4; ++dc) {
+    const uint32_t full = pp.full + 8 * pp.slot, stage = pp.ring + pp.slot * (STAGE_DBL * 8);
+    mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+    mbar_expect_tx(full, 8192u + 512u * nen);
+    bulk_g2s(stage, s.v + (size_t)dc * 1024, 8192u, full);
+    if (s.en[0]) bulk_g2s(stage + 8192u, s.t[0] + (size_t)dc * 64, 512u, full);
+    if (s.en[1]) bulk_g2s(stage + 8704u, s.t[1] + (size_t)dc * 64, 512u, full);
+    pp.advance();
+  }
+  for (int lg = 0; lg < 2 * nl4; ++lg) {
+    const uint32_t full = pp.full + 8 * pp.slot, stage = pp.ring + pp.slot * (STAGE_DBL * 8);
+    mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+    mbar_expect_tx(full, 4608u * nen);
+    if (s.en[0]) {
+      bulk_g2s(stage, s.hh[0] + (size_t)lg * 512, 4096u, full);
+      bulk_g2s(stage + 8192u, s.u[0] + (size_t)(lg >> 1) * 64, 512u, full);
+    }
+    if (s.en[1]) {
+      bulk_g2s(stage + 4096u, s.hh[1] + (size_t)lg * 512, 4096u, full);
+      bulk_g2s(stage + 8704u, s.u[1] + (size_t)(lg >> 1) * 64, 512u, full);
+    }
+    pp.advance();
+  }
+}
+
+// consumer side of one step; acc[h][mf][bi][co][e]
+__device__ __forceinline__ void consume_step(double (&acc)[2][2][2][2][2], const double* ring, Pipe& pp,
+                                             int nk4, int nl4, int en0, int en1, int warp, int lane) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+      for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+        for (int co = 0; co < 2; ++co) acc[h][mf][bi][co][0] = acc[h][mf][bi][co][1] = 0.0;
+
+  // ---- particle contraction: W[a,b,c] += sum_d T2[a,d,x,y] V[b,c,d,z]
+  for (int dc = 0; dc < nk4; ++dc) {
+    const double* st = ring + pp.slot * STAGE_DBL;
+    mbar_wait(pp.full + 8 * pp.slot, pp.phase);
+    double bf[2][2], af[2][2];
+#pragma unroll
+    for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+      for (int co = 0; co < 2; ++co) bf[bi][co] = st[((warp + 8 * bi) * 2 + co) * 32 + lane];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf) {
+      af[0][mf] = st[1024 + mf * 32 + lane];
+      af[1][mf] = st[1088 + mf * 32 + lane];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
+    pp.advance();
+    if (en0) {
+#pragma unroll
+      for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+          for (int co = 0; co < 2; ++co)
+            dmma(acc[0][mf][bi][co][0], acc[0][mf][bi][co][1], af[0][mf], bf[bi][co]);
+    }
+    if (en1) {
+#pragma unroll
+      for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+          for (int co = 0; co < 2; ++co)
+            dmma(acc[1][mf][bi][co][0], acc[1][mf][bi][co][1], af[1][mf], bf[bi][co]);
+    }
+  }
+  // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); sub-stage g covers b = w + 8g
+  for (int lc = 0; lc < nl4; ++lc) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const double* st = ring + pp.slot * STAGE_DBL;
+      mbar_wait(pp.full + 8 * pp.slot, pp.phase);
+      double af[2][2], uf[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf) af[h][mf] = st[h * 512 + warp * 64 + mf * 32 + lane];
+#pragma unroll
+        for (int co = 0; co < 2; ++co) uf[h][co] = st[1024 + h * 64 + co * 32 + lane];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
+      pp.advance();
+      if (en0) {
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+          for (int co = 0; co < 2; ++co)
+            dmma(acc[0][mf][g][co][0], acc[0][mf][g][co][1], af[0][mf], uf[0][co]);
+      }
+      if (en1) {
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+          for (int co = 0; co < 2; ++co)
+            dmma(acc[1][mf][g][co][0], acc[1][mf][g][co][1], af[1][mf], uf[1][co]);
+      }
+    }
+  }
+}
+
+// X_tau[x] += W_h[w] with x_n = w_{q[n]}
+__device__ __forceinline__ void scatter_add(double* Xs, const double (&a)[2][2][2][2], int tau, int q0,
+                                            int q1, int q2, int warp, int lane) {
+  double* X = Xs + tau * XT_DBL;
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+    for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+      for (int co = 0; co < 2; ++co)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int la = 8 * mf + (lane >> 2), lb = warp + 8 * bi, lc = 8 * co + 2 * (lane & 3) + e;
+          const int idx = xt_index(sel3(la, lb, lc, q0), sel3(la, lb, lc, q1), sel3(la, lb, lc, q2));
+          X[idx] += a[mf][bi][co][e];
+        }
+}
+
+__device__ __forceinline__ void carve_smem(unsigned char* raw, double*& Xs, double*& ring, double*& Qs,
+                                           double*& tv, double*& red, uint64_t*& bars) {
+  Xs = reinterpret_cast<double*>(raw);
+  ring = Xs + 6 * XT_DBL;
+  Qs = ring + NSTAGE * STAGE_DBL;
+  tv = Qs + 3 * 256;
+  red = tv + 96;
+  bars = reinterpret_cast<uint64_t*>(red + 8);
+}
+constexpr int FUSED_SMEM_BYTES = (6 * XT_DBL + NSTAGE * STAGE_DBL + 3 * 256 + 96 + 8) * 8 + 2 * NSTAGE * 8;
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *Xs, *ring, *Qs, *tv, *red;
+  uint64_t* bars;
+  carve_smem(smem_raw, Xs, ring, Qs, tv, red, bars);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk4 = p.d.nk4, nl4 = p.d.nl4, v = p.d.v, o = p.d.o;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(smem_u32(bars + s), 1);
+      mbar_init(smem_u32(bars + NSTAGE + s), NCONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp < NCONSUMER_WARPS)
+    for (int idx = tid; idx < 6 * XT_DBL; idx += NCONSUMER_WARPS * 32) Xs[idx] = 0.0;
+  __syncthreads();
+
+  Pipe pp;
+  pp.ring = smem_u32(ring);
+  pp.full = smem_u32(bars);
+  pp.empty = smem_u32(bars + NSTAGE);
+  pp.slot = 0;
+  pp.phase = 0;
+
+  if (warp == NCONSUMER_WARPS) {
+    // ===== producer warp: one lane streams operand stages =====
+    if (lane != 0) return;
+    for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const int t = (int)(item / p.norbits), orb = (int)(item - (long long)t * p.norbits);
+      const int4 tr = p.triples[t];
+      const uchar4 ob = p.orbits[orb];
+      const PtClassTable& tab = c_tab[tr.w][ob.w];
+      for (int s = 0; s < tab.nsteps; ++s) {
+        const StepSrc src = make_step_src(p, tab.steps[s], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
+        produce_step(src, pp, nk4, nl4);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+    const int t = (int)(item / p.norbits), orb = (int)(item - (long long)t * p.norbits);
+    const int4 tr = p.triples[t];
+    const uchar4 ob = p.orbits[orb];
+    const PtClassTable& tab = c_tab[tr.w][ob.w];
+    const int hi = tr.x, hj = tr.y, hk = tr.z;
+
+    for (int s = 0; s < tab.nsteps; ++s) {
+      const PtStep& st = tab.steps[s];
+      double acc[2][2][2][2][2];
+      consume_step(acc, ring, pp, nk4, nl4, st.h[0].en, st.h[1].en, warp, lane);
+      // the two halves may target the same X tile (orbits with coinciding ranges) through
+      // different index permutations, so their read-modify-writes are separated by a barrier
+      if (st.h[0].en) scatter_add(Xs, acc[0], st.h[0].tau, st.h[0].q0, st.h[0].q1, st.h[0].q2, warp, lane);
+      consumer_barrier();
+      if (st.h[1].en) scatter_add(Xs, acc[1], st.h[1].tau, st.h[1].q0, st.h[1].q1, st.h[1].q2, warp, lane);
+      consumer_barrier();
+    }
+
+    // ---- epilogue: E_item = sum_tiles sum_x (Xd + Sd)[x] * (sum_nu c_nu Xd[x o nu]) / D[x]
+    const double e3 = p.epsi[hi] + p.epsi[hj] + p.epsi[hk];
+    const int pm = tab.pmask;
+    double e_acc = 0.0;
+    for (int tl = 0; tl < tab.ntiles; ++tl) {
+      const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
+      const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
+      const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
+      {
+        // singles: Sd = 1/2 (t_i[a] Qa[b,c] + t_j[b] Qb[a,c] + t_k[c] Qc[a,b])
+        // (getSinglesContribution :81-85 summed over the distinct hole permutations)
+        const int u = tid & 15, w_ = tid >> 4;
+        const double* P = p.pphh;
+        const size_t vv = (size_t)v;
+        double qa = 0.0, qb = 0.0, qc = 0.0;
+        {
+          const size_t g1 = gb0 + u, g2 = gc0 + w_;
+          if (g1 < vv && g2 < vv) {
+            if (pm & 1) qa += P[g1 + vv * (g2 + vv * (hj + (size_t)o * hk))];
+            if (pm & 8) qa += P[g2 + vv * (g1 + vv * (hk + (size_t)o * hj))];
+          }
+        }
+        {
+          const size_t g0 = ga0 + u, g2 = gc0 + w_;
+          if (g0 < vv && g2 < vv) {
+            if (pm & 2) qb += P[g0 + vv * (g2 + vv * (hi + (size_t)o * hk))];
+            if (pm & 4) qb += P[g2 + vv * (g0 + vv * (hk + (size_t)o * hi))];
+          }
+        }
+        {
+          const size_t g0 = ga0 + u, g1 = gb0 + w_;
+          if (g0 < vv && g1 < vv) {
+            if (pm & 16) qc += P[g0 + vv * (g1 + vv * (hi + (size_t)o * hj))];
+            if (pm & 32) qc += P[g1 + vv * (g0 + vv * (hj + (size_t)o * hi))];
+          }
+        }
+        Qs[tid] = qa;
+        Qs[256 + tid] = qb;
+        Qs[512 + tid] = qc;
+        if (tid < 48) {
+          const int which = tid >> 4, uu = tid & 15;
+          const int g = (which == 0 ? ga0 : (which == 1 ? gb0 : gc0)) + uu;
+          const int hh = which == 0 ? hi : (which == 1 ? hj : hk);
+          tv[tid] = g < v ? p.t1[g + (size_t)v * hh] : 0.0;
+          tv[48 + tid] = g < v ? p.epsa[g] : 0.0;
+        }
+      }
+      consumer_barrier();
+      const double* Xt = Xs + tl * XT_DBL;
+      const int8_t* nb = tab.nbr[tl];
+#pragma unroll 4
+      for (int r = 0; r < 16; ++r) {
+        const int pt_ = tid + 256 * r;
+        const int x0 = pt_ & 15, x1 = (pt_ >> 4) & 15, x2 = pt_ >> 8;
+        const bool valid = (ga0 + x0 < v) && (gb0 + x1 < v) && (gc0 + x2 < v);
+        // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}
+        double zn = tab.coef[0] * Xs[nb[0] * XT_DBL + xt_index(x0, x1, x2)];
+        zn += tab.coef[1] * Xs[nb[1] * XT_DBL + xt_index(x1, x0, x2)];
+        zn += tab.coef[2] * Xs[nb[2] * XT_DBL + xt_index(x1, x2, x0)];
+        zn += tab.coef[3] * Xs[nb[3] * XT_DBL + xt_index(x0, x2, x1)];
+        zn += tab.coef[4] * Xs[nb[4] * XT_DBL + xt_index(x2, x0, x1)];
+        zn += tab.coef[5] * Xs[nb[5] * XT_DBL + xt_index(x2, x1, x0)];
+        const double sd = 0.5 * (tv[x0] * Qs[x1 + 16 * x2] + tv[16 + x1] * Qs[256 + x0 + 16 * x2] +
+                                 tv[32 + x2] * Qs[512 + x0 + 16 * x1]);
+        const double rr = Xt[xt_index(x0, x1, x2)] + sd;
+        const double dd = e3 - tv[48 + x0] - tv[64 + x1] - tv[80 + x2];
+        if (valid) e_acc += rr * zn / dd;
+      }
+      consumer_barrier();
+    }
+    // warp-shuffle reduction, then one atomic per item
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e_acc += __shfl_down_sync(0xffffffffu, e_acc, off);
+    if (lane == 0) red[warp] = e_acc;
+    for (int idx = tid; idx < 6 * XT_DBL; idx += NCONSUMER_WARPS * 32) Xs[idx] = 0.0;
+    consumer_barrier();
+    if (tid == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int w = 0; w < NCONSUMER_WARPS; ++w) s += red[w];
+      atomicAdd(p.e_triple + t, s);
+    }
+  }
+}
+
+// ------------------------------------------------ debug: one W tile via the main loop
+__global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const FusedParams p, WTileJob job,
+                                                                    double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *Xs, *ring, *Qs, *tv, *red;
+  uint64_t* bars;
+  carve_smem(smem_raw, Xs, ring, Qs, tv, red, bars);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(smem_u32(bars + s), 1);
+      mbar_init(smem_u32(bars + NSTAGE + s), NCONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  Pipe pp;
+  pp.ring = smem_u32(ring);
+  pp.full = smem_u32(bars);
+  pp.empty = smem_u32(bars + NSTAGE);
+  pp.slot = 0;
+  pp.phase = 0;
+  StepSrc src;
+  src.v = p.Vt + vt_tile_off(p.d, job.z, job.Q, job.R);
+  src.t[0] = src.t[1] = p.Tt + tt_panel_off(p.d, job.x, job.y, job.P);
+  src.hh[0] = src.hh[1] = p.T2h + t2h_block_off(p.d, job.x, job.P, job.Q);
+  src.u[0] = src.u[1] = p.Ut + ut_panel_off(p.d, job.y, job.z, job.R);
+  src.en[0] = 1;
+  src.en[1] = 0;
+  if (warp == NCONSUMER_WARPS) {
+    if (lane == 0) produce_step(src, pp, p.d.nk4, p.d.nl4);
+    return;
+  }
+  double acc[2][2][2][2][2];
+  consume_step(acc, ring, pp, p.d.nk4, p.d.nl4, 1, 0, warp, lane);
+#pragma unroll
+  for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+    for (int bi = 0; bi < 2; ++bi)
+#pragma unroll
+      for (int co = 0; co < 2; ++co)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int la = 8 * mf + (lane >> 2), lb = warp + 8 * bi, lc = 8 * co + 2 * (lane & 3) + e;
+          out[la + 16 * (lb + 16 * lc)] = acc[0][mf][bi][co][e];
+        }
+}
+
+// ------------------------------------------------------------------- launchers
+cudaError_t fused_configure(int* smem_bytes_out) {
+  cudaError_t e = cudaFuncSetAttribute(pt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FUSED_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pt_w_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           FUSED_SMEM_BYTES);
+  if (smem_bytes_out) *smem_bytes_out = FUSED_SMEM_BYTES;
+  return e;
+}
+
+cudaError_t launch_fused(const FusedParams& p, int grid, cudaStream_t s) {
+  if (p.nitems <= 0) return cudaSuccess;
+  pt_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_w_tile(const FusedParams& p, WTileJob job, double* d_out, cudaStream_t s) {
+  pt_w_tile_kernel<<<1, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(p, job, d_out);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------ FP64 issue-rate microbenchmarks
+// mode 0: DMMA.8x8x4 (8 independent accumulator fragments per warp)
+// mode 1: DFMA (16 independent chains per thread)
+__global__ void __launch_bounds__(1024) bench_fp64_kernel(int mode, int iters, double* sink,
+                                                          unsigned long long* cycles) {
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = 0.0;
+  const long long t0 = clock64();
+  if (mode == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dmma(c[j][0], c[j][1], a, b);
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j][0] = fma(a, c[j][0], b);
+        c[j][1] = fma(b, c[j][1], a);
+      }
+    }
+  }
+  const long long t1 = clock64();
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  if (s == 123.456) sink[0] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+}
+
+cudaError_t launch_bench_fp64(int mode, int blocks, int warps, int iters, double* d_sink,
+                              unsigned long long* d_cycles, cudaStream_t s) {
+  bench_fp64_kernel<<<blocks, warps * 32, 0, s>>>(mode, iters, d_sink, d_cycles);
+  return cudaGetLastError();
+}
+
+}  // namespace pt

@@ -1,0 +1,161 @@
+"""Seeded synthetic inputs for the (T) step.
+
+Counter-based generator (splitmix64 of (seed, tensor id, linear index)) so
+every process -- the CPU oracle run, each GPU rank, the golden-fixture script
+-- produces bit-identical raw values without shipping tensors around.
+
+Two families:
+
+* ``make_inputs(o, v, kind="vertex")``: "UEG-style" closed-shell inputs.  A
+  complex Coulomb vertex Gamma[F,p,q] with real and imaginary parts each
+  symmetric in (p,q); PPHH / HHHP / PPPH integrals built from it with the
+  reference's real-integral formulas
+  (/root/reference/src/algorithms/CoulombIntegralsFromVertex.cxx:402-403,
+  416-417, 430-431; particles are the last v states, :121-136), MP2-like
+  doubles T2 = Vpphh / (e_i+e_j-e_a-e_b) and small random singles.  These carry
+  the physical permutational symmetries.
+* ``kind="random"``: every tensor filled with independent uniforms, no symmetry
+  at all.  The reference algorithm assumes none, so neither may the kernels.
+
+All arrays are Fortran-ordered (column-major, first index fastest), i.e. the
+CTF global layout the C ABI expects (include/sisi4s_pt.h).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        z = (x + np.uint64(0x9E3779B97F4A7C15)) & _M64
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _M64
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _M64
+        return z ^ (z >> np.uint64(31))
+
+
+def _stream(seed: int, tensor_id: int, n: int, lane: int = 0) -> np.ndarray:
+    """n uniforms in [0,1) for (seed, tensor_id, lane)."""
+    with np.errstate(over="ignore"):
+        base = _splitmix64(np.array([seed], dtype=np.uint64))[0]
+        base = _splitmix64(np.array([base ^ np.uint64(tensor_id * 2 + lane)],
+                                    dtype=np.uint64))[0]
+        idx = np.arange(n, dtype=np.uint64)
+        z = _splitmix64(idx * np.uint64(0xD1342543DE82EF95) + base)
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def uniform(seed: int, tensor_id: int, shape) -> np.ndarray:
+    """Uniform(-1,1), Fortran order."""
+    n = int(np.prod(shape))
+    u = 2.0 * _stream(seed, tensor_id, n) - 1.0
+    return u.reshape(shape, order="F")
+
+
+def normal(seed: int, tensor_id: int, shape) -> np.ndarray:
+    """N(0,1) by Box-Muller, Fortran order."""
+    n = int(np.prod(shape))
+    u1 = _stream(seed, tensor_id, n, lane=0)
+    u2 = _stream(seed, tensor_id, n, lane=1)
+    r = np.sqrt(-2.0 * np.log1p(-u1))  # u1 in [0,1) -> 1-u1 in (0,1]
+    g = r * np.cos(2.0 * np.pi * u2)
+    return g.reshape(shape, order="F")
+
+
+@dataclass
+class TriplesInputs:
+    o: int
+    v: int
+    epsi: np.ndarray   # [o]
+    epsa: np.ndarray   # [v]
+    T1: np.ndarray     # [v,o]       CcsdSinglesAmplitudes
+    T2: np.ndarray     # [v,v,o,o]   CcsdDoublesAmplitudes
+    Vpphh: np.ndarray  # [v,v,o,o]   PPHHCoulombIntegrals
+    Vhhhp: np.ndarray  # [o,o,o,v]   HHHPCoulombIntegrals
+    Vppph: np.ndarray  # [v,v,v,o]   PPPHCoulombIntegrals
+    Gamma: np.ndarray | None = None  # [NF,Np,Np] complex CoulombVertex (kind="vertex")
+    ccsd_energy: float = 0.0
+
+    def args(self):
+        return (self.epsi, self.epsa, self.T1, self.T2, self.Vpphh, self.Vhhhp, self.Vppph)
+
+
+def eigenenergies(o: int, v: int):
+    return np.linspace(-2.0, -0.5, o), np.linspace(0.5, 4.0, v)
+
+
+def default_kappa(o: int, v: int) -> float:
+    """Vertex amplitude that keeps |E(T)| of order 1e-2..1e-1 Eh.
+
+    E scales as kappa^8 (V ~ kappa^2, T2 ~ kappa^2, W ~ kappa^4); at unit kappa
+    |E| ~ 2.2e-3 o^1.96 v^2.68 (least-squares fit to the oracle at six shapes
+    between (5,19) and (10,40)).
+    """
+    return float((0.05 / (2.2e-3 * o ** 1.96 * v ** 2.68)) ** 0.125)
+
+
+def make_vertex(o: int, v: int, seed: int = 2026, nf: int | None = None,
+                kappa: float | None = None) -> np.ndarray:
+    """Complex vertex Gamma[F,p,q], Re and Im parts each symmetric in (p,q)."""
+    nf = 2 * v if nf is None else nf
+    np_ = o + v
+    kappa = default_kappa(o, v) if kappa is None else kappa
+    g = 1.0 / (1.0 + np.arange(np_) / np_)
+    damp = g[None, :, None] * g[None, None, :]
+    R = normal(seed, 1, (nf, np_, np_)) * (kappa / np.sqrt(nf))
+    R = (R + R.transpose(0, 2, 1)) * damp
+    I = normal(seed, 2, (nf, np_, np_)) * (0.3 * kappa / np.sqrt(nf))
+    I = (I + I.transpose(0, 2, 1)) * damp
+    return np.asfortranarray(R + 1j * I)
+
+
+def integrals_from_vertex(Gamma: np.ndarray, o: int, v: int):
+    """CoulombIntegralsFromVertex.cxx:399-433 (real integrals), as GEMMs."""
+    nf, np_, _ = Gamma.shape
+    a0 = np_ - v
+    out = []
+    Gr, Gi = np.ascontiguousarray(Gamma.real), np.ascontiguousarray(Gamma.imag)
+    Vpphh = np.zeros((v, v, o, o))
+    Vhhhp = np.zeros((o, o, o, v))
+    Vppph = np.zeros((v, v, v, o))
+    for G in (Gr, Gi):
+        Gij = G[:, :o, :o].reshape(nf, o * o)      # [F,(i,k)]
+        Gai = G[:, a0:, :o].reshape(nf, v * o)     # [F,(a,i)]
+        Gab = G[:, a0:, a0:].reshape(nf, v * v)    # [F,(a,c)]
+        # Vabij[a,b,i,j] = G[G,a,i] G[G,b,j]
+        Vpphh += (Gai.T @ Gai).reshape(v, o, v, o).transpose(0, 2, 1, 3)
+        # Vijka[i,j,k,a] = G[G,i,k] G[G,a,j]
+        Vhhhp += (Gij.T @ Gai).reshape(o, o, v, o).transpose(0, 3, 1, 2)
+        # Vabci[a,b,c,i] = G[G,a,c] G[G,b,i]
+        Vppph += (Gab.T @ Gai).reshape(v, v, v, o).transpose(0, 2, 1, 3)
+    del out
+    return (np.asfortranarray(Vpphh), np.asfortranarray(Vhhhp), np.asfortranarray(Vppph))
+
+
+def make_inputs(o: int, v: int, seed: int = 2026, kind: str = "vertex",
+                nf: int | None = None, kappa: float | None = None) -> TriplesInputs:
+    epsi, epsa = eigenenergies(o, v)
+    if kind == "vertex":
+        Gamma = make_vertex(o, v, seed, nf, kappa)
+        Vpphh, Vhhhp, Vppph = integrals_from_vertex(Gamma, o, v)
+        D2 = (epsi[None, None, :, None] + epsi[None, None, None, :]
+              - epsa[:, None, None, None] - epsa[None, :, None, None])
+        T2 = np.asfortranarray(Vpphh / D2)
+        rms = float(np.sqrt(np.mean(T2 * T2)))
+        T1 = np.asfortranarray(normal(seed, 3, (v, o)) * rms)
+        ccsd = float(np.einsum("abij,abij->", 2.0 * Vpphh - Vpphh.transpose(1, 0, 2, 3), T2))
+        return TriplesInputs(o, v, epsi, epsa, T1, T2, Vpphh, Vhhhp, Vppph, Gamma, ccsd)
+    if kind == "random":
+        s = 0.3
+        return TriplesInputs(
+            o, v, epsi, epsa,
+            T1=s * uniform(seed, 11, (v, o)),
+            T2=s * uniform(seed, 12, (v, v, o, o)),
+            Vpphh=s * uniform(seed, 13, (v, v, o, o)),
+            Vhhhp=s * uniform(seed, 14, (o, o, o, v)),
+            Vppph=s * uniform(seed, 15, (v, v, v, o)),
+            ccsd_energy=-1.0)
+    raise ValueError(f"unknown kind {kind!r}")

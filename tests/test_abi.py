@@ -1,0 +1,90 @@
+"""CPU checks of the drop-in boundary: the shared library loads and exports every
+symbol include/sisi4s_pt.h declares, host-only entry points behave, and without a
+CUDA device the product path fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from sisi4s_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+
+
+def test_header_symbols_all_exported():
+    _ensure_built()
+    with open(os.path.join(ROOT, "include", "sisi4s_pt.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b(pt_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_host_only_entry_points():
+    _ensure_built()
+    lib = _lib.load()
+    assert b"sm_100a" in lib.pt_version()
+    assert lib.pt_num_triples(40) == 11480 and lib.pt_num_triples(5) == 35
+    # partition covers the enumeration exactly, contiguously, for every rank count
+    for o in (1, 2, 5, 20, 40):
+        for n in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(n):
+                b, e = C.c_int64(), C.c_int64()
+                assert lib.pt_partition(o, n, r, C.byref(b), C.byref(e)) == 0
+                assert b.value == prev and e.value >= b.value
+                prev = e.value
+            assert prev == lib.pt_num_triples(o)
+    b, e = C.c_int64(), C.c_int64()
+    assert lib.pt_partition(5, 2, 2, C.byref(b), C.byref(e)) == -1
+    assert b"pt_partition" in lib.pt_last_error()
+
+
+def test_partition_is_weight_balanced():
+    _ensure_built()
+    lib = _lib.load()
+    o, n = 40, 8
+    tr = [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)]
+    w = [[6, 3, 3, 1][(i == j) + 2 * (j == k)] for (i, j, k) in tr]
+    loads = []
+    for r in range(n):
+        b, e = C.c_int64(), C.c_int64()
+        lib.pt_partition(o, n, r, C.byref(b), C.byref(e))
+        loads.append(sum(w[b.value:e.value]))
+    assert max(loads) <= 1.01 * (sum(w) / n)
+
+
+def test_no_cpu_fallback_without_gpu():
+    from conftest import gpu_available
+    if gpu_available():
+        pytest.skip("CUDA device present")
+    _ensure_built()
+    from sisi4s_b200.triples import TriplesEngine
+    with pytest.raises(_lib.PtError) as ei:
+        TriplesEngine(5, 19)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_plugin_mirror_argument_errors():
+    # mirrors Algorithm::getTensorArgument / setRealArgument error behaviour
+    # (reference src/algorithms/Algorithm.cxx:37-55, 364-367)
+    import numpy as np
+    from sisi4s_b200.triples import AlgorithmFactory, SisiException
+    data = {"eps": np.zeros(3)}
+    alg = AlgorithmFactory.create("CcsdPerturbativeTriples", {"HoleEigenEnergies": "$eps"}, data)
+    assert alg is not None and alg.getName() == "CcsdPerturbativeTriples"
+    with pytest.raises(SisiException, match="Missing argument: ParticleEigenEnergies"):
+        alg.getTensorArgument("ParticleEigenEnergies")
+    with pytest.raises(SisiException, match="Missing argument: CcsdPerturbativeTriplesEnergy"):
+        alg.setRealArgument("CcsdPerturbativeTriplesEnergy", 1.0)
+    assert AlgorithmFactory.create("NoSuchAlgorithm", {}, data) is None
+    assert AlgorithmFactory.create("PerturbativeTriples", {}, data).getName() == "PerturbativeTriples"
