@@ -116,23 +116,28 @@ def integrals_from_vertex(Gamma: np.ndarray, o: int, v: int):
     """CoulombIntegralsFromVertex.cxx:399-433 (real integrals), as GEMMs."""
     nf, np_, _ = Gamma.shape
     a0 = np_ - v
-    out = []
     Gr, Gi = np.ascontiguousarray(Gamma.real), np.ascontiguousarray(Gamma.imag)
     Vpphh = np.zeros((v, v, o, o))
     Vhhhp = np.zeros((o, o, o, v))
-    Vppph = np.zeros((v, v, v, o))
+    Vppph = np.empty((v, v, v, o), order="F")
+    parts = []
     for G in (Gr, Gi):
         Gij = G[:, :o, :o].reshape(nf, o * o)      # [F,(i,k)]
         Gai = G[:, a0:, :o].reshape(nf, v * o)     # [F,(a,i)]
-        Gab = G[:, a0:, a0:].reshape(nf, v * v)    # [F,(a,c)]
         # Vabij[a,b,i,j] = G[G,a,i] G[G,b,j]
         Vpphh += (Gai.T @ Gai).reshape(v, o, v, o).transpose(0, 2, 1, 3)
         # Vijka[i,j,k,a] = G[G,i,k] G[G,a,j]
         Vhhhp += (Gij.T @ Gai).reshape(o, o, v, o).transpose(0, 3, 1, 2)
-        # Vabci[a,b,c,i] = G[G,a,c] G[G,b,i]
-        Vppph += (Gab.T @ Gai).reshape(v, v, v, o).transpose(0, 2, 1, 3)
-    del out
-    return (np.asfortranarray(Vpphh), np.asfortranarray(Vhhhp), np.asfortranarray(Vppph))
+        # operands of Vabci, laid out so each hole slab is one GEMM
+        Gca = np.ascontiguousarray(G[:, a0:, a0:].transpose(0, 2, 1)).reshape(nf, v * v)  # [F,(c,a)]
+        Gib = np.ascontiguousarray(G[:, a0:, :o].transpose(2, 1, 0))                       # [i,b,F]
+        parts.append((Gca, Gib))
+    # Vabci[a,b,c,i] = G[G,a,c] G[G,b,i], one column-major v^3 slab per hole i
+    for i in range(o):
+        X = parts[0][1][i] @ parts[0][0]
+        X += parts[1][1][i] @ parts[1][0]          # [b,(c,a)]
+        Vppph[:, :, :, i] = X.reshape(v, v, v).transpose(2, 0, 1)
+    return (np.asfortranarray(Vpphh), np.asfortranarray(Vhhhp), Vppph)
 
 
 def make_inputs(o: int, v: int, seed: int = 2026, kind: str = "vertex",
