@@ -1,0 +1,14 @@
+"""Short (40,300) run of the fused kernel for ncu captures: one pt_run over a small
+range of sorted triples (cold start, inputs resident)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sisi4s_b200 import synthetic as S
+from sisi4s_b200.triples import TriplesEngine
+
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
+with TriplesEngine(40, 300) as eng:
+    eng.set_inputs(*inp.args())
+    r = eng.run(b, b + n)
+    print("E", r.energy, "s_kernel", r.seconds_kernel, "TF/s", r.flops / r.seconds_kernel * 1e-12)
