@@ -43,6 +43,7 @@ struct PtHandle_ {
   int engine = PT_ENGINE_FUSED;
   int keep_raw = 0;
   int grid = 0;
+  int order = 1;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // raw device tensors
@@ -204,6 +205,9 @@ int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "grid")) {
     if (value < 0) return fail(PT_ERR_INVALID, "grid %lld", (long long)value);
     h->grid = (int)value;
+  } else if (!strcmp(key, "order")) {
+    if (value != 0 && value != 1) return fail(PT_ERR_INVALID, "order %lld", (long long)value);
+    h->order = (int)value;
   } else {
     return fail(PT_ERR_INVALID, "pt_set_option: unknown key '%s'", key);
   }
@@ -436,6 +440,8 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
       CU(cudaMemsetAsync(d_e, 0, list.size() * sizeof(double), h->stream));
       FusedParams p = make_params(h);
       p.triples = d_list;
+      p.ntriples = (int)list.size();
+      p.order = h->order;
       p.nitems = (long long)list.size() * h->norbits;
       p.e_triple = d_e;
       int grid = h->grid > 0 ? h->grid : h->sm_count;

@@ -86,9 +86,24 @@ struct FusedParams {
   const int4* triples;    // (i,j,k,class) of the sorted triples of this run
   const uchar4* orbits;   // (A,B,C,class), A>=B>=C
   int norbits;
+  int ntriples;
+  int order;              // 0: triple-major (orbit fastest), 1: orbit-major (triple fastest; L2 reuse of PPPH tiles)
   long long nitems;       // ntriples * norbits
   double* e_triple;       // [ntriples], accumulated with atomicAdd
 };
+
+// item -> (triple, orbit).  Orbit-major order makes the CTAs that run concurrently work on
+// the SAME particle-range orbit of neighbouring hole triples, so they stream the same PPPH
+// tiles (z; Q,R) at the same time and those are served by L2 instead of HBM.
+__device__ __forceinline__ void decode_item(const FusedParams& p, long long item, int& t, int& orb) {
+  if (p.order == 0) {
+    t = (int)(item / p.norbits);
+    orb = (int)(item - (long long)t * p.norbits);
+  } else {
+    orb = (int)(item / p.ntriples);
+    t = (int)(item - (long long)orb * p.ntriples);
+  }
+}
 
 // one W tile job of the debug kernel
 struct WTileJob { int x, y, z, P, Q, R; };

@@ -24,10 +24,10 @@
 //   A (8x4, row):  a  = A[lane>>2][lane&3]
 //   B (4x8, col):  b  = B[lane&3][lane>>2]
 //   C (8x8):       c0,c1 = C[lane>>2][2*(lane&3) + {0,1}]
-// Warp w of the 8 consumer warps owns, of the stacked 32 x (16b x 16c) output,
-// all 4 row fragments (half h = 0,1; mf = 0,1) and the columns
-// b in {w, w+8}, c-octet co in {0,1}:  acc[h][mf][bi][co][e] is
-//   W_h[la = 8 mf + (lane>>2), lb = w + 8 bi, lc = 8 co + 2 (lane&3) + e].
+// The 8 consumer warps form two groups of four; group h = warp>>2 owns half h of the
+// stacked 32 x (16b x 16c) output (one 16^3 W tile), warp wq = warp&3 of the group the
+// columns b in {wq, wq+4, wq+8, wq+12}:  acc[mf][bi][co][e] is
+//   W_h[la = 8 mf + (lane>>2), lb = wq + 4 bi, lc = 8 co + 2 (lane&3) + e].
 #include "pt_common.cuh"
 #include "pt_tables.h"
 
@@ -156,105 +156,183 @@ __device__ __forceinline__ void produce_step(const StepSrc& s, Pipe& pp, int nk4
   }
 }
 
-// consumer side of one step; acc[h][mf][bi][co][e]
-__device__ __forceinline__ void consume_step(double (&acc)[2][2][2][2][2], const double* ring, Pipe& pp,
-                                             int nk4, int nl4, int en0, int en1, int warp, int lane) {
+// consumer side of one step for one warp.  The 8 consumer warps form two groups of four:
+// group h = warp>>2 owns half h of the stacked step (one 16 x 256 W tile), warp wq = warp&3 of
+// the group owns the columns b in {wq, wq+4, wq+8, wq+12}:  acc[mf][bi][co][e] is
+//   W_h[la = 8 mf + (lane>>2), lb = wq + 4 bi, lc = 8 co + 2 (lane&3) + e].
+// The two warps that share an SM sub-partition (w, w+4) therefore belong to different groups
+// and scatter into different X tiles, so no CTA barrier is needed between steps and one
+// group's scatter overlaps the other group's DMMA stream.
+__device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], const double* ring, Pipe& pp,
+                                             int nk4, int nl4, int en, int h, int wq, int lane) {
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
-    for (int mf = 0; mf < 2; ++mf)
+    for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
-      for (int bi = 0; bi < 2; ++bi)
-#pragma unroll
-        for (int co = 0; co < 2; ++co) acc[h][mf][bi][co][0] = acc[h][mf][bi][co][1] = 0.0;
+      for (int co = 0; co < 2; ++co) acc[mf][bi][co][0] = acc[mf][bi][co][1] = 0.0;
+
+  if (!en) {
+    // disabled half: keep the stage accounting going
+    const int n = nk4 + 2 * nl4;
+    for (int s = 0; s < n; ++s) {
+      mbar_wait(pp.full + 8 * pp.slot, pp.phase);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
+      pp.advance();
+    }
+    return;
+  }
 
   // ---- particle contraction: W[a,b,c] += sum_d T2[a,d,x,y] V[b,c,d,z]
   for (int dc = 0; dc < nk4; ++dc) {
     const double* st = ring + pp.slot * STAGE_DBL;
     mbar_wait(pp.full + 8 * pp.slot, pp.phase);
-    double bf[2][2], af[2][2];
+    double bf[4][2], af[2];
 #pragma unroll
-    for (int bi = 0; bi < 2; ++bi)
+    for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
-      for (int co = 0; co < 2; ++co) bf[bi][co] = st[((warp + 8 * bi) * 2 + co) * 32 + lane];
+      for (int co = 0; co < 2; ++co) bf[bi][co] = st[((wq + 4 * bi) * 2 + co) * 32 + lane];
 #pragma unroll
-    for (int mf = 0; mf < 2; ++mf) {
-      af[0][mf] = st[1024 + mf * 32 + lane];
-      af[1][mf] = st[1088 + mf * 32 + lane];
-    }
+    for (int mf = 0; mf < 2; ++mf) af[mf] = st[1024 + h * 64 + mf * 32 + lane];
     __syncwarp();
     if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
     pp.advance();
-    if (en0) {
 #pragma unroll
-      for (int mf = 0; mf < 2; ++mf)
+    for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
-        for (int bi = 0; bi < 2; ++bi)
+      for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
-          for (int co = 0; co < 2; ++co)
-            dmma(acc[0][mf][bi][co][0], acc[0][mf][bi][co][1], af[0][mf], bf[bi][co]);
-    }
-    if (en1) {
-#pragma unroll
-      for (int mf = 0; mf < 2; ++mf)
-#pragma unroll
-        for (int bi = 0; bi < 2; ++bi)
-#pragma unroll
-          for (int co = 0; co < 2; ++co)
-            dmma(acc[1][mf][bi][co][0], acc[1][mf][bi][co][1], af[1][mf], bf[bi][co]);
-    }
+        for (int co = 0; co < 2; ++co) dmma(acc[mf][bi][co][0], acc[mf][bi][co][1], af[mf], bf[bi][co]);
   }
-  // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); sub-stage g covers b = w + 8g
+  // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); sub-stage g covers
+  //      b = 8g .. 8g+7, of which this warp owns b = 8g + wq + 4j  (bi = 2g + j)
   for (int lc = 0; lc < nl4; ++lc) {
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const double* st = ring + pp.slot * STAGE_DBL;
       mbar_wait(pp.full + 8 * pp.slot, pp.phase);
-      double af[2][2], uf[2][2];
+      double af[2][2], uf[2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int mf = 0; mf < 2; ++mf) af[h][mf] = st[h * 512 + warp * 64 + mf * 32 + lane];
+        for (int mf = 0; mf < 2; ++mf) af[j][mf] = st[h * 512 + (wq + 4 * j) * 64 + mf * 32 + lane];
 #pragma unroll
-        for (int co = 0; co < 2; ++co) uf[h][co] = st[1024 + h * 64 + co * 32 + lane];
-      }
+      for (int co = 0; co < 2; ++co) uf[co] = st[1024 + h * 64 + co * 32 + lane];
       __syncwarp();
       if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
       pp.advance();
-      if (en0) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
           for (int co = 0; co < 2; ++co)
-            dmma(acc[0][mf][g][co][0], acc[0][mf][g][co][1], af[0][mf], uf[0][co]);
-      }
-      if (en1) {
-#pragma unroll
-        for (int mf = 0; mf < 2; ++mf)
-#pragma unroll
-          for (int co = 0; co < 2; ++co)
-            dmma(acc[1][mf][g][co][0], acc[1][mf][g][co][1], af[1][mf], uf[1][co]);
-      }
+            dmma(acc[mf][2 * g + j][co][0], acc[mf][2 * g + j][co][1], af[j][mf], uf[co]);
     }
   }
 }
 
-// X_tau[x] += W_h[w] with x_n = w_{q[n]}
-__device__ __forceinline__ void scatter_add(double* Xs, const double (&a)[2][2][2][2], int tau, int q0,
-                                            int q1, int q2, int warp, int lane) {
-  double* X = Xs + tau * XT_DBL;
+__host__ __device__ constexpr int bitswap13(int v) { return (v & 5) | ((v & 2) << 2) | ((v & 8) >> 2); }
+__host__ __device__ constexpr int csel3(int a, int b, int c, int idx) { return idx == 0 ? a : (idx == 1 ? b : c); }
+
+// X_tau[x] += W_h[w] with x_n = w_{q[n]}, q compile-time.  A W coordinate splits into a
+// per-thread part (g, wq, 2*t4) and a per-register part (8mf, 4bi, 8co+e) with disjoint bits, and
+// the swizzle of xt_index is XOR-linear, so  idx = (tl ^ cl) + tbase + cbase  with cl, cbase
+// immediates: one LOP + one IADD per element.  All 16 loads are issued before the stores (the
+// 16 targets of a thread are distinct elements).
+template <int Q0, int Q1, int Q2>
+__device__ __forceinline__ void scatter_add_q(double* X, const double (&a)[2][4][2][2], int wq, int lane) {
+  const int g = lane >> 2, t2 = 2 * (lane & 3);
+  const int tx0 = csel3(g, wq, t2, Q0), tx1 = csel3(g, wq, t2, Q1), tx2 = csel3(g, wq, t2, Q2);
+  const int tl = tx0 ^ tx1 ^ bitswap13(tx2);
+  double* Xb = X + 16 * tx1 + 256 * tx2;
 #pragma unroll
-  for (int mf = 0; mf < 2; ++mf)
+  for (int mf = 0; mf < 2; ++mf) {
+    double old[4][2][2];
 #pragma unroll
-    for (int bi = 0; bi < 2; ++bi)
+    for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
       for (int co = 0; co < 2; ++co)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int la = 8 * mf + (lane >> 2), lb = warp + 8 * bi, lc = 8 * co + 2 * (lane & 3) + e;
-          const int idx = xt_index(sel3(la, lb, lc, q0), sel3(la, lb, lc, q1), sel3(la, lb, lc, q2));
-          X[idx] += a[mf][bi][co][e];
+          constexpr int dummy = 0; (void)dummy;
+          const int c0 = csel3(8 * mf, 4 * bi, 8 * co + e, Q0), c1 = csel3(8 * mf, 4 * bi, 8 * co + e, Q1),
+                    c2 = csel3(8 * mf, 4 * bi, 8 * co + e, Q2);
+          const int cl = c0 ^ c1 ^ bitswap13(c2);
+          old[bi][co][e] = Xb[(tl ^ cl) + 16 * c1 + 256 * c2];
         }
+#pragma unroll
+    for (int bi = 0; bi < 4; ++bi)
+#pragma unroll
+      for (int co = 0; co < 2; ++co)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c0 = csel3(8 * mf, 4 * bi, 8 * co + e, Q0), c1 = csel3(8 * mf, 4 * bi, 8 * co + e, Q1),
+                    c2 = csel3(8 * mf, 4 * bi, 8 * co + e, Q2);
+          const int cl = c0 ^ c1 ^ bitswap13(c2);
+          Xb[(tl ^ cl) + 16 * c1 + 256 * c2] = old[bi][co][e] + a[mf][bi][co][e];
+        }
+  }
+}
+
+__device__ __forceinline__ void scatter_add(double* Xs, const double (&a)[2][4][2][2], int tau, int q0, int q1,
+                                            int wq, int lane) {
+  double* X = Xs + tau * XT_DBL;
+  switch (q0 * 3 + q1) {
+    case 1: scatter_add_q<0, 1, 2>(X, a, wq, lane); break;
+    case 2: scatter_add_q<0, 2, 1>(X, a, wq, lane); break;
+    case 3: scatter_add_q<1, 0, 2>(X, a, wq, lane); break;
+    case 5: scatter_add_q<1, 2, 0>(X, a, wq, lane); break;
+    case 6: scatter_add_q<2, 0, 1>(X, a, wq, lane); break;
+    default: scatter_add_q<2, 1, 0>(X, a, wq, lane); break;
+  }
+}
+
+// staging values of one X tile of the epilogue (singles-term operands + eigenvalues) into
+// registers; issued one tile ahead so the global-load latency hides behind the point loop.
+//   Sd = 1/2 (t_i[a] Qa[b,c] + t_j[b] Qb[a,c] + t_k[c] Qc[a,b])
+// (getSinglesContribution, CcsdPerturbativeTriples.cxx:81-85, summed over the distinct hole
+// permutations; pm = mask of those)
+__device__ __forceinline__ void epi_stage_load(const FusedParams& p, const PtClassTable& tab, uchar4 ob, int tl,
+                                               int hi, int hj, int hk, int pm, int tid, double& sq0,
+                                               double& sq1, double& sq2, double& stv0, double& stv1) {
+  const int v = p.d.v, o = p.d.o;
+  const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
+  const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
+  const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
+  const int u = tid & 15, w_ = tid >> 4;
+  const double* P = p.pphh;
+  const size_t vv = (size_t)v;
+  sq0 = sq1 = sq2 = 0.0;
+  {
+    const size_t g1 = gb0 + u, g2 = gc0 + w_;
+    if (g1 < vv && g2 < vv) {
+      if (pm & 1) sq0 += __ldg(P + g1 + vv * (g2 + vv * (hj + (size_t)o * hk)));
+      if (pm & 8) sq0 += __ldg(P + g2 + vv * (g1 + vv * (hk + (size_t)o * hj)));
+    }
+  }
+  {
+    const size_t g0 = ga0 + u, g2 = gc0 + w_;
+    if (g0 < vv && g2 < vv) {
+      if (pm & 2) sq1 += __ldg(P + g0 + vv * (g2 + vv * (hi + (size_t)o * hk)));
+      if (pm & 4) sq1 += __ldg(P + g2 + vv * (g0 + vv * (hk + (size_t)o * hi)));
+    }
+  }
+  {
+    const size_t g0 = ga0 + u, g1 = gb0 + w_;
+    if (g0 < vv && g1 < vv) {
+      if (pm & 16) sq2 += __ldg(P + g0 + vv * (g1 + vv * (hi + (size_t)o * hj)));
+      if (pm & 32) sq2 += __ldg(P + g1 + vv * (g0 + vv * (hj + (size_t)o * hi)));
+    }
+  }
+  if (tid < 48) {
+    const int which = tid >> 4, uu = tid & 15;
+    const int g = (which == 0 ? ga0 : (which == 1 ? gb0 : gc0)) + uu;
+    const int hh = which == 0 ? hi : (which == 1 ? hj : hk);
+    stv0 = g < v ? __ldg(p.t1 + g + (size_t)v * hh) : 0.0;
+    stv1 = g < v ? __ldg(p.epsa + g) : 0.0;
+  }
 }
 
 __device__ __forceinline__ void carve_smem(unsigned char* raw, double*& Xs, double*& ring, double*& Qs,
@@ -300,7 +378,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
     // ===== producer warp: one lane streams operand stages =====
     if (lane != 0) return;
     for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-      const int t = (int)(item / p.norbits), orb = (int)(item - (long long)t * p.norbits);
+      int t, orb;
+      decode_item(p, item, t, orb);
       const int4 tr = p.triples[t];
       const uchar4 ob = p.orbits[orb];
       const PtClassTable& tab = c_tab[tr.w][ob.w];
@@ -313,8 +392,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   }
 
   // ===== consumer warps =====
+  const int grp = warp >> 2, wq = warp & 3;
+  // without CTA barriers between steps, two read-modify-writes of one X element by different
+  // warps are ordered through the stage ring (a warp can run at most NSTAGE stages ahead of
+  // the slowest one); that needs steps of more than NSTAGE stages
+  const bool step_sync_always = (nk4 + 2 * nl4) < 2 * NSTAGE;
   for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-    const int t = (int)(item / p.norbits), orb = (int)(item - (long long)t * p.norbits);
+    int t, orb;
+    decode_item(p, item, t, orb);
     const int4 tr = p.triples[t];
     const uchar4 ob = p.orbits[orb];
     const PtClassTable& tab = c_tab[tr.w][ob.w];
@@ -322,83 +407,71 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
 
     for (int s = 0; s < tab.nsteps; ++s) {
       const PtStep& st = tab.steps[s];
-      double acc[2][2][2][2][2];
-      consume_step(acc, ring, pp, nk4, nl4, st.h[0].en, st.h[1].en, warp, lane);
-      // the two halves may target the same X tile (orbits with coinciding ranges) through
-      // different index permutations, so their read-modify-writes are separated by a barrier
-      if (st.h[0].en) scatter_add(Xs, acc[0], st.h[0].tau, st.h[0].q0, st.h[0].q1, st.h[0].q2, warp, lane);
-      consumer_barrier();
-      if (st.h[1].en) scatter_add(Xs, acc[1], st.h[1].tau, st.h[1].q0, st.h[1].q1, st.h[1].q2, warp, lane);
-      consumer_barrier();
+      const PtHalf& hf = st.h[grp];
+      double acc[2][4][2][2];
+      consume_step(acc, ring, pp, nk4, nl4, hf.en, grp, wq, lane);
+      // the halves of a step target different X tiles except in orbits with coinciding
+      // ranges; only then (or for very short steps) are the two scatters separated by barriers
+      const bool sync = step_sync_always || (st.h[0].en && st.h[1].en && st.h[0].tau == st.h[1].tau);
+      if (!sync) {
+        if (hf.en) scatter_add(Xs, acc, hf.tau, hf.q0, hf.q1, wq, lane);
+      } else {
+        if (grp == 0 && hf.en) scatter_add(Xs, acc, hf.tau, hf.q0, hf.q1, wq, lane);
+        consumer_barrier();
+        if (grp == 1 && hf.en) scatter_add(Xs, acc, hf.tau, hf.q0, hf.q1, wq, lane);
+        consumer_barrier();
+      }
     }
 
     // ---- epilogue: E_item = sum_tiles sum_x (Xd + Sd)[x] * (sum_nu c_nu Xd[x o nu]) / D[x]
     const double e3 = p.epsi[hi] + p.epsi[hj] + p.epsi[hk];
     const int pm = tab.pmask;
     double e_acc = 0.0;
+    // staging values of one tile (singles term operands + eigenvalues), prefetched into
+    // registers one tile ahead so that the global-load latency hides behind the point loop
+    double sq0, sq1, sq2, stv0 = 0.0, stv1 = 0.0;
+    epi_stage_load(p, tab, ob, 0, hi, hj, hk, pm, tid, sq0, sq1, sq2, stv0, stv1);
+    consumer_barrier();  // all scatters of the item are done
     for (int tl = 0; tl < tab.ntiles; ++tl) {
       const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
       const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
       const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
-      {
-        // singles: Sd = 1/2 (t_i[a] Qa[b,c] + t_j[b] Qb[a,c] + t_k[c] Qc[a,b])
-        // (getSinglesContribution :81-85 summed over the distinct hole permutations)
-        const int u = tid & 15, w_ = tid >> 4;
-        const double* P = p.pphh;
-        const size_t vv = (size_t)v;
-        double qa = 0.0, qb = 0.0, qc = 0.0;
-        {
-          const size_t g1 = gb0 + u, g2 = gc0 + w_;
-          if (g1 < vv && g2 < vv) {
-            if (pm & 1) qa += P[g1 + vv * (g2 + vv * (hj + (size_t)o * hk))];
-            if (pm & 8) qa += P[g2 + vv * (g1 + vv * (hk + (size_t)o * hj))];
-          }
-        }
-        {
-          const size_t g0 = ga0 + u, g2 = gc0 + w_;
-          if (g0 < vv && g2 < vv) {
-            if (pm & 2) qb += P[g0 + vv * (g2 + vv * (hi + (size_t)o * hk))];
-            if (pm & 4) qb += P[g2 + vv * (g0 + vv * (hk + (size_t)o * hi))];
-          }
-        }
-        {
-          const size_t g0 = ga0 + u, g1 = gb0 + w_;
-          if (g0 < vv && g1 < vv) {
-            if (pm & 16) qc += P[g0 + vv * (g1 + vv * (hi + (size_t)o * hj))];
-            if (pm & 32) qc += P[g1 + vv * (g0 + vv * (hj + (size_t)o * hi))];
-          }
-        }
-        Qs[tid] = qa;
-        Qs[256 + tid] = qb;
-        Qs[512 + tid] = qc;
-        if (tid < 48) {
-          const int which = tid >> 4, uu = tid & 15;
-          const int g = (which == 0 ? ga0 : (which == 1 ? gb0 : gc0)) + uu;
-          const int hh = which == 0 ? hi : (which == 1 ? hj : hk);
-          tv[tid] = g < v ? p.t1[g + (size_t)v * hh] : 0.0;
-          tv[48 + tid] = g < v ? p.epsa[g] : 0.0;
-        }
+      Qs[tid] = sq0;
+      Qs[256 + tid] = sq1;
+      Qs[512 + tid] = sq2;
+      if (tid < 48) {
+        tv[tid] = stv0;
+        tv[48 + tid] = stv1;
       }
       consumer_barrier();
+      if (tl + 1 < tab.ntiles) epi_stage_load(p, tab, ob, tl + 1, hi, hj, hk, pm, tid, sq0, sq1, sq2, stv0, stv1);
       const double* Xt = Xs + tl * XT_DBL;
       const int8_t* nb = tab.nbr[tl];
+      const double* X1 = Xs + nb[1] * XT_DBL;
+      const double* X2 = Xs + nb[2] * XT_DBL;
+      const double* X3 = Xs + nb[3] * XT_DBL;
+      const double* X4 = Xs + nb[4] * XT_DBL;
+      const double* X5 = Xs + nb[5] * XT_DBL;
+      const double c0 = tab.coef[0], c1 = tab.coef[1], c2 = tab.coef[2], c3 = tab.coef[3], c4 = tab.coef[4],
+                   c5 = tab.coef[5];
+      const int x0 = tid & 15, x1 = tid >> 4;
+      const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
+      const double d01 = e3 - tv[48 + x0] - tv[64 + x1];
+      const double t0 = tv[x0], t1v = tv[16 + x1];
 #pragma unroll 4
-      for (int r = 0; r < 16; ++r) {
-        const int pt_ = tid + 256 * r;
-        const int x0 = pt_ & 15, x1 = (pt_ >> 4) & 15, x2 = pt_ >> 8;
-        const bool valid = (ga0 + x0 < v) && (gb0 + x1 < v) && (gc0 + x2 < v);
-        // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}
-        double zn = tab.coef[0] * Xs[nb[0] * XT_DBL + xt_index(x0, x1, x2)];
-        zn += tab.coef[1] * Xs[nb[1] * XT_DBL + xt_index(x1, x0, x2)];
-        zn += tab.coef[2] * Xs[nb[2] * XT_DBL + xt_index(x1, x2, x0)];
-        zn += tab.coef[3] * Xs[nb[3] * XT_DBL + xt_index(x0, x2, x1)];
-        zn += tab.coef[4] * Xs[nb[4] * XT_DBL + xt_index(x2, x0, x1)];
-        zn += tab.coef[5] * Xs[nb[5] * XT_DBL + xt_index(x2, x1, x0)];
-        const double sd = 0.5 * (tv[x0] * Qs[x1 + 16 * x2] + tv[16 + x1] * Qs[256 + x0 + 16 * x2] +
+      for (int x2 = 0; x2 < 16; ++x2) {
+        // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}; nbr[tl][0] == tl (identity)
+        const double xd = Xt[xt_index(x0, x1, x2)];
+        double zn = c0 * xd;
+        zn += c1 * X1[xt_index(x1, x0, x2)];
+        zn += c2 * X2[xt_index(x1, x2, x0)];
+        zn += c3 * X3[xt_index(x0, x2, x1)];
+        zn += c4 * X4[xt_index(x2, x0, x1)];
+        zn += c5 * X5[xt_index(x2, x1, x0)];
+        const double sd = 0.5 * (t0 * Qs[x1 + 16 * x2] + t1v * Qs[256 + x0 + 16 * x2] +
                                  tv[32 + x2] * Qs[512 + x0 + 16 * x1]);
-        const double rr = Xt[xt_index(x0, x1, x2)] + sd;
-        const double dd = e3 - tv[48 + x0] - tv[64 + x1] - tv[80 + x2];
-        if (valid) e_acc += rr * zn / dd;
+        const double dd = d01 - tv[80 + x2];
+        if (valid01 && (gc0 + x2 < v)) e_acc += (xd + sd) * zn / dd;
       }
       consumer_barrier();
     }
@@ -450,18 +523,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
     if (lane == 0) produce_step(src, pp, p.d.nk4, p.d.nl4);
     return;
   }
-  double acc[2][2][2][2][2];
-  consume_step(acc, ring, pp, p.d.nk4, p.d.nl4, 1, 0, warp, lane);
+  const int grp = warp >> 2, wq = warp & 3;
+  double acc[2][4][2][2];
+  consume_step(acc, ring, pp, p.d.nk4, p.d.nl4, grp == 0, grp, wq, lane);
+  if (grp != 0) return;
 #pragma unroll
   for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
-    for (int bi = 0; bi < 2; ++bi)
+    for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
       for (int co = 0; co < 2; ++co)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int la = 8 * mf + (lane >> 2), lb = warp + 8 * bi, lc = 8 * co + 2 * (lane & 3) + e;
-          out[la + 16 * (lb + 16 * lc)] = acc[0][mf][bi][co][e];
+          const int la = 8 * mf + (lane >> 2), lb = wq + 4 * bi, lc = 8 * co + 2 * (lane & 3) + e;
+          out[la + 16 * (lb + 16 * lc)] = acc[mf][bi][co][e];
         }
 }
 
