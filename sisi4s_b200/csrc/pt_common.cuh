@@ -88,6 +88,7 @@ struct FusedParams {
   int norbits;
   int ntriples;
   int order;              // 0: triple-major (orbit fastest), 1: orbit-major (triple fastest; L2 reuse of PPPH tiles)
+  int prefetch;           // L2 prefetch distance of the producer warp in stages (0 = off)
   long long nitems;       // ntriples * norbits
   double* e_triple;       // [ntriples], accumulated with atomicAdd
 };

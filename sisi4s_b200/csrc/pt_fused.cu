@@ -128,21 +128,31 @@ struct Pipe {
   }
 };
 
-// producer side of one step: nk4 particle-contraction stages, then 2*nl4 hole stages
-__device__ __forceinline__ void produce_step(const StepSrc& s, Pipe& pp, int nk4, int nl4) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// Stage j of a step: j < nk4 is particle chunk j (one 8 KB slab-tile chunk + the enabled
+// 512 B T2 panels), otherwise hole sub-stage lg = j - nk4 (per enabled half one 4 KB T2h
+// chunk + one 512 B HHHP panel chunk).
+__device__ __forceinline__ void issue_stage(const StepSrc& s, int j, int nk4, uint32_t stage, uint32_t full) {
   const uint32_t nen = (uint32_t)(s.en[0] + s.en[1]);
-  for (int dc = 0; dc < nk4; ++dc) {
-    const uint32_t full = pp.full + 8 * pp.slot, stage = pp.ring + pp.slot * (STAGE_DBL * 8);
-    mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+  if (j < nk4) {
     mbar_expect_tx(full, 8192u + 512u * nen);
-    bulk_g2s(stage, s.v + (size_t)dc * 1024, 8192u, full);
-    if (s.en[0]) bulk_g2s(stage + 8192u, s.t[0] + (size_t)dc * 64, 512u, full);
-    if (s.en[1]) bulk_g2s(stage + 8704u, s.t[1] + (size_t)dc * 64, 512u, full);
-    pp.advance();
-  }
-  for (int lg = 0; lg < 2 * nl4; ++lg) {
-    const uint32_t full = pp.full + 8 * pp.slot, stage = pp.ring + pp.slot * (STAGE_DBL * 8);
-    mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+    bulk_g2s(stage, s.v + (size_t)j * 1024, 8192u, full);
+    if (s.en[0]) bulk_g2s(stage + 8192u, s.t[0] + (size_t)j * 64, 512u, full);
+    if (s.en[1]) bulk_g2s(stage + 8704u, s.t[1] + (size_t)j * 64, 512u, full);
+  } else {
+    const int lg = j - nk4;
     mbar_expect_tx(full, 4608u * nen);
     if (s.en[0]) {
       bulk_g2s(stage, s.hh[0] + (size_t)lg * 512, 4096u, full);
@@ -152,7 +162,90 @@ __device__ __forceinline__ void produce_step(const StepSrc& s, Pipe& pp, int nk4
       bulk_g2s(stage + 4096u, s.hh[1] + (size_t)lg * 512, 4096u, full);
       bulk_g2s(stage + 8704u, s.u[1] + (size_t)(lg >> 1) * 64, 512u, full);
     }
+  }
+}
+// L2 prefetch of the operands of stage j (the small panels in 4 KB pieces every 8th stage)
+__device__ __forceinline__ void prefetch_stage(const StepSrc& s, int j, int nk4, int nl4) {
+  if (j < nk4) {
+    prefetch_l2(s.v + (size_t)j * 1024, 8192u);
+    if ((j & 7) == 0) {
+      const uint32_t bytes = (uint32_t)min(8, nk4 - j) * 512u;
+      if (s.en[0]) prefetch_l2(s.t[0] + (size_t)j * 64, bytes);
+      if (s.en[1]) prefetch_l2(s.t[1] + (size_t)j * 64, bytes);
+    }
+  } else {
+    const int lg = j - nk4;
+    if (s.en[0]) prefetch_l2(s.hh[0] + (size_t)lg * 512, 4096u);
+    if (s.en[1]) prefetch_l2(s.hh[1] + (size_t)lg * 512, 4096u);
+    if (lg == 0) {
+      if (s.en[0]) prefetch_l2(s.u[0], (uint32_t)nl4 * 512u);
+      if (s.en[1]) prefetch_l2(s.u[1], (uint32_t)nl4 * 512u);
+    }
+  }
+}
+
+// Position in the CTA's stream of operand stages (item -> step -> stage); warp-uniform.
+struct StageIter {
+  long long item;
+  int s, j, nsteps;
+  bool valid;
+  int4 tr;
+  uchar4 ob;
+  int tc, oc;
+  StepSrc src;
+  __device__ __forceinline__ void load_item(const FusedParams& p) {
+    valid = item < p.nitems;
+    if (!valid) return;
+    int t, orb;
+    decode_item(p, item, t, orb);
+    tr = p.triples[t];
+    ob = p.orbits[orb];
+    tc = tr.w;
+    oc = ob.w;
+    nsteps = c_tab[tc][oc].nsteps;
+    s = 0;
+    j = 0;
+    src = make_step_src(p, c_tab[tc][oc].steps[0], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
+  }
+  __device__ __forceinline__ void next(const FusedParams& p, int nst, int stride) {
+    if (++j < nst) return;
+    j = 0;
+    if (++s < nsteps) {
+      src = make_step_src(p, c_tab[tc][oc].steps[s], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
+      return;
+    }
+    item += stride;
+    load_item(p);
+  }
+};
+
+
+// producer warp: all 32 lanes run the (uniform) stream bookkeeping, one elected lane
+// issues the copies.  A second iterator runs p.prefetch stages ahead and pulls the same
+// operands into L2, so that an HBM miss never sits on the 3-stage ring's critical path.
+__device__ __forceinline__ void producer_loop(const FusedParams& p, Pipe& pp, long long first_item, int stride) {
+  const int nk4 = p.d.nk4, nl4 = p.d.nl4, nst = nk4 + 2 * nl4;
+  StageIter ld, pf;
+  ld.item = first_item;
+  ld.load_item(p);
+  pf = ld;
+  const bool leader = elect_one();
+  const int pfd = p.prefetch;  // L2 prefetch distance in stages (0 = off)
+  if (pfd == 0) pf.valid = false;
+  for (int n = 0; n < pfd && pf.valid; ++n) {
+    if (leader) prefetch_stage(pf.src, pf.j, nk4, nl4);
+    pf.next(p, nst, stride);
+  }
+  while (ld.valid) {
+    if (pf.valid) {
+      if (leader) prefetch_stage(pf.src, pf.j, nk4, nl4);
+      pf.next(p, nst, stride);
+    }
+    const uint32_t full = pp.full + 8 * pp.slot, stage = pp.ring + pp.slot * (STAGE_DBL * 8);
+    mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+    if (leader) issue_stage(ld.src, ld.j, nk4, stage, full);
     pp.advance();
+    ld.next(p, nst, stride);
   }
 }
 
@@ -184,11 +277,13 @@ __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], const do
     return;
   }
 
+  // Operand fragments are double-buffered in registers: the fragments of stage n+1 are
+  // fetched (and its ring slot released) before the DMMAs of stage n issue, which makes the
+  // register file a fourth pipeline stage.
   // ---- particle contraction: W[a,b,c] += sum_d T2[a,d,x,y] V[b,c,d,z]
-  for (int dc = 0; dc < nk4; ++dc) {
+  auto ld_p = [&](double (&bf)[4][2], double (&af)[2]) {
     const double* st = ring + pp.slot * STAGE_DBL;
     mbar_wait(pp.full + 8 * pp.slot, pp.phase);
-    double bf[4][2], af[2];
 #pragma unroll
     for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
@@ -198,37 +293,61 @@ __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], const do
     __syncwarp();
     if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
     pp.advance();
+  };
+  auto mma_p = [&](const double (&bf)[4][2], const double (&af)[2]) {
 #pragma unroll
     for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
       for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
         for (int co = 0; co < 2; ++co) dmma(acc[mf][bi][co][0], acc[mf][bi][co][1], af[mf], bf[bi][co]);
-  }
+  };
   // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); sub-stage g covers
   //      b = 8g .. 8g+7, of which this warp owns b = 8g + wq + 4j  (bi = 2g + j)
-  for (int lc = 0; lc < nl4; ++lc) {
+  auto ld_h = [&](double (&af)[2][2], double (&uf)[2]) {
+    const double* st = ring + pp.slot * STAGE_DBL;
+    mbar_wait(pp.full + 8 * pp.slot, pp.phase);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const double* st = ring + pp.slot * STAGE_DBL;
-      mbar_wait(pp.full + 8 * pp.slot, pp.phase);
-      double af[2][2], uf[2];
+    for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int mf = 0; mf < 2; ++mf) af[j][mf] = st[h * 512 + (wq + 4 * j) * 64 + mf * 32 + lane];
 #pragma unroll
-        for (int mf = 0; mf < 2; ++mf) af[j][mf] = st[h * 512 + (wq + 4 * j) * 64 + mf * 32 + lane];
-#pragma unroll
-      for (int co = 0; co < 2; ++co) uf[co] = st[1024 + h * 64 + co * 32 + lane];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
-      pp.advance();
+    for (int co = 0; co < 2; ++co) uf[co] = st[1024 + h * 64 + co * 32 + lane];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
+    pp.advance();
+  };
+  {
+    double bfA[4][2], afA[2], bfB[4][2], afB[2];
+    double hfA[2][2], ufA[2], hfB[2][2], ufB[2];
+    ld_p(bfA, afA);
+    int dc = 0;
+    for (; dc + 1 < nk4; dc += 2) {
+      ld_p(bfB, afB);
+      mma_p(bfA, afA);
+      if (dc + 2 < nk4) ld_p(bfA, afA); else ld_h(hfA, ufA);
+      mma_p(bfB, afB);
+    }
+    if (nk4 & 1) {
+      ld_h(hfA, ufA);
+      mma_p(bfA, afA);
+    }
+    // hfA/ufA hold hole sub-stage (lc = 0, g = 0)
+    for (int lc = 0; lc < nl4; ++lc) {
+      ld_h(hfB, ufB);  // (lc, g = 1)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
-          for (int co = 0; co < 2; ++co)
-            dmma(acc[mf][2 * g + j][co][0], acc[mf][2 * g + j][co][1], af[j][mf], uf[co]);
+          for (int co = 0; co < 2; ++co) dmma(acc[mf][j][co][0], acc[mf][j][co][1], hfA[j][mf], ufA[co]);
+      if (lc + 1 < nl4) ld_h(hfA, ufA);  // (lc + 1, g = 0)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+          for (int co = 0; co < 2; ++co) dmma(acc[mf][2 + j][co][0], acc[mf][2 + j][co][1], hfB[j][mf], ufB[co]);
     }
   }
 }
@@ -375,19 +494,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   pp.phase = 0;
 
   if (warp == NCONSUMER_WARPS) {
-    // ===== producer warp: one lane streams operand stages =====
-    if (lane != 0) return;
-    for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-      int t, orb;
-      decode_item(p, item, t, orb);
-      const int4 tr = p.triples[t];
-      const uchar4 ob = p.orbits[orb];
-      const PtClassTable& tab = c_tab[tr.w][ob.w];
-      for (int s = 0; s < tab.nsteps; ++s) {
-        const StepSrc src = make_step_src(p, tab.steps[s], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
-        produce_step(src, pp, nk4, nl4);
-      }
-    }
+    // ===== producer warp =====
+    producer_loop(p, pp, blockIdx.x, gridDim.x);
     return;
   }
 
@@ -520,7 +628,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
   src.en[0] = 1;
   src.en[1] = 0;
   if (warp == NCONSUMER_WARPS) {
-    if (lane == 0) produce_step(src, pp, p.d.nk4, p.d.nl4);
+    const bool leader = elect_one();
+    const int nst = p.d.nk4 + 2 * p.d.nl4;
+    for (int j = 0; j < nst; ++j) {
+      mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+      if (leader) issue_stage(src, j, p.d.nk4, pp.ring + pp.slot * (STAGE_DBL * 8), pp.full + 8 * pp.slot);
+      pp.advance();
+    }
     return;
   }
   const int grp = warp >> 2, wq = warp & 3;
