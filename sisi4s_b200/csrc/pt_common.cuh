@@ -30,7 +30,7 @@ namespace pt {
 
 constexpr int TILE = 16;
 constexpr int STAGE_DBL = 1152;            // doubles per pipeline stage (9216 B)
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 16;              // operand ring depth (X tiles live in TMEM, so the ring owns the smem)
 constexpr int XT_DBL = TILE * TILE * TILE; // one X tile
 constexpr int NCONSUMER_WARPS = 8;
 constexpr int FUSED_THREADS = (NCONSUMER_WARPS + 1) * 32;

@@ -7,13 +7,16 @@
 //      tile of a PPPH slab (K = v) plus the hole term (K = o) on FP64 tensor
 //      cores (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4), operands streamed from the
 //      pre-tiled HBM layouts by cp.async.bulk (TMA engine, SASS UBLKCP) through a
-//      3-stage mbarrier ring filled by a dedicated producer warp;
-//   2. adds each 16^3 W tile, index-permuted, into the orbit's X tiles, which
-//      live in shared memory for the whole item (6 x 32 KB) -- the v^3 triples
-//      blocks are never written to HBM;
-//   3. epilogue: permutational symmetrisation (six index permutations with the
-//      spin factors), singles term, eigenvalue denominator, warp-shuffle
-//      reduction, one atomicAdd per item into the triple's energy.
+//      16-stage mbarrier ring filled by a dedicated producer warp;
+//   2. adds each 16^3 W tile, index-permuted, into the orbit's six X tiles, which
+//      live in TENSOR MEMORY (6 x 32 KB of the SM's 256 KB TMEM, tcgen05.ld/st ->
+//      SASS LDTM/STTM) for the whole item, so that shared memory belongs to the
+//      operand ring -- the v^3 triples blocks are never written to HBM.  The index
+//      permutation goes through a per-group 32 KB staging tile in shared memory;
+//   3. epilogue: the X tiles are copied from TMEM into the (drained) ring region, then
+//      permutational symmetrisation (six index permutations with the spin factors),
+//      singles term, eigenvalue denominator, warp-shuffle reduction, one atomicAdd per
+//      item into the triple's energy.
 //
 // This replaces, per sorted triple, getDoublesContribution / the permutation
 // accumulate / divide / spin-factor symmetrise / energy dot of the reference
@@ -71,11 +74,45 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void consumer_barrier() {
   asm volatile("bar.sync 1, %0;" ::"n"(NCONSUMER_WARPS * 32) : "memory");
 }
+__device__ __forceinline__ void group_barrier(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(NCONSUMER_WARPS * 16) : "memory");
+}
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
+
+// ---- tensor memory (TMEM) as the home of the X accumulator tiles ------------------------
+// tcgen05.ld/st .32x32b: thread i of warp w addresses TMEM lane 32*(w%4)+i and N consecutive
+// 32-bit columns (verified on hardware by tools/probes/tmem_probe.cu).  A double occupies two
+// columns (lo, hi).  X tile tau, element n = x0 + 16 x1 + 256 x2 lives in lane n & 127,
+// columns 64 tau + 2 (n >> 7) + {0,1}.
+#define TM_R16(r, o) "=r"(r[o+0]),"=r"(r[o+1]),"=r"(r[o+2]),"=r"(r[o+3]),"=r"(r[o+4]),"=r"(r[o+5]),"=r"(r[o+6]),"=r"(r[o+7]),"=r"(r[o+8]),"=r"(r[o+9]),"=r"(r[o+10]),"=r"(r[o+11]),"=r"(r[o+12]),"=r"(r[o+13]),"=r"(r[o+14]),"=r"(r[o+15])
+#define TM_I16(r, o) "r"(r[o+0]),"r"(r[o+1]),"r"(r[o+2]),"r"(r[o+3]),"r"(r[o+4]),"r"(r[o+5]),"r"(r[o+6]),"r"(r[o+7]),"r"(r[o+8]),"r"(r[o+9]),"r"(r[o+10]),"r"(r[o+11]),"r"(r[o+12]),"r"(r[o+13]),"r"(r[o+14]),"r"(r[o+15])
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : TM_R16(r, 0), TM_R16(r, 16)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      TM_I16(r, 0), TM_I16(r, 16)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_COLS_PER_TILE = 64;
 
 __device__ __forceinline__ int sel3(int a, int b, int c, int idx) {
   return idx == 0 ? a : (idx == 1 ? b : c);
@@ -223,7 +260,8 @@ struct StageIter {
 // producer warp: all 32 lanes run the (uniform) stream bookkeeping, one elected lane
 // issues the copies.  A second iterator runs p.prefetch stages ahead and pulls the same
 // operands into L2, so that an HBM miss never sits on the 3-stage ring's critical path.
-__device__ __forceinline__ void producer_loop(const FusedParams& p, Pipe& pp, long long first_item, int stride) {
+__device__ __forceinline__ void producer_loop(const FusedParams& p, Pipe& pp, uint32_t go_bar, long long first_item,
+                                              int stride) {
   const int nk4 = p.d.nk4, nl4 = p.d.nl4, nst = nk4 + 2 * nl4;
   StageIter ld, pf;
   ld.item = first_item;
@@ -236,7 +274,13 @@ __device__ __forceinline__ void producer_loop(const FusedParams& p, Pipe& pp, lo
     if (leader) prefetch_stage(pf.src, pf.j, nk4, nl4);
     pf.next(p, nst, stride);
   }
+  uint32_t items_started = 0;
   while (ld.valid) {
+    if (ld.s == 0 && ld.j == 0) {
+      // the epilogue of the previous item copies the X tiles over the ring: wait until it is done
+      if (items_started > 0) mbar_wait(go_bar, (items_started - 1) & 1);
+      ++items_started;
+    }
     if (pf.valid) {
       if (leader) prefetch_stage(pf.src, pf.j, nk4, nl4);
       pf.next(p, nst, stride);
@@ -355,32 +399,19 @@ __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], const do
 __host__ __device__ constexpr int bitswap13(int v) { return (v & 5) | ((v & 2) << 2) | ((v & 8) >> 2); }
 __host__ __device__ constexpr int csel3(int a, int b, int c, int idx) { return idx == 0 ? a : (idx == 1 ? b : c); }
 
-// X_tau[x] += W_h[w] with x_n = w_{q[n]}, q compile-time.  A W coordinate splits into a
-// per-thread part (g, wq, 2*t4) and a per-register part (8mf, 4bi, 8co+e) with disjoint bits, and
-// the swizzle of xt_index is XOR-linear, so  idx = (tl ^ cl) + tbase + cbase  with cl, cbase
-// immediates: one LOP + one IADD per element.  All 16 loads are issued before the stores (the
-// 16 targets of a thread are distinct elements).
+// S[x] = W_h[w] with x_n = w_{q[n]}, q compile-time: the warp's W fragment is written,
+// index-permuted, into the group's staging tile (same XOR-swizzled layout as the X tiles of the
+// epilogue).  A W coordinate splits into a per-thread part (g, wq, 2*t4) and a per-register part
+// (8mf, 4bi, 8co+e) with disjoint bits, and the swizzle of xt_index is XOR-linear, so
+// idx = (tl ^ cl) + tbase + cbase with cl, cbase immediates.
 template <int Q0, int Q1, int Q2>
-__device__ __forceinline__ void scatter_add_q(double* X, const double (&a)[2][4][2][2], int wq, int lane) {
+__device__ __forceinline__ void stage_store_q(double* S, const double (&a)[2][4][2][2], int wq, int lane) {
   const int g = lane >> 2, t2 = 2 * (lane & 3);
   const int tx0 = csel3(g, wq, t2, Q0), tx1 = csel3(g, wq, t2, Q1), tx2 = csel3(g, wq, t2, Q2);
   const int tl = tx0 ^ tx1 ^ bitswap13(tx2);
-  double* Xb = X + 16 * tx1 + 256 * tx2;
+  double* Sb = S + 16 * tx1 + 256 * tx2;
 #pragma unroll
-  for (int mf = 0; mf < 2; ++mf) {
-    double old[4][2][2];
-#pragma unroll
-    for (int bi = 0; bi < 4; ++bi)
-#pragma unroll
-      for (int co = 0; co < 2; ++co)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          constexpr int dummy = 0; (void)dummy;
-          const int c0 = csel3(8 * mf, 4 * bi, 8 * co + e, Q0), c1 = csel3(8 * mf, 4 * bi, 8 * co + e, Q1),
-                    c2 = csel3(8 * mf, 4 * bi, 8 * co + e, Q2);
-          const int cl = c0 ^ c1 ^ bitswap13(c2);
-          old[bi][co][e] = Xb[(tl ^ cl) + 16 * c1 + 256 * c2];
-        }
+  for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
     for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
@@ -390,22 +421,51 @@ __device__ __forceinline__ void scatter_add_q(double* X, const double (&a)[2][4]
           const int c0 = csel3(8 * mf, 4 * bi, 8 * co + e, Q0), c1 = csel3(8 * mf, 4 * bi, 8 * co + e, Q1),
                     c2 = csel3(8 * mf, 4 * bi, 8 * co + e, Q2);
           const int cl = c0 ^ c1 ^ bitswap13(c2);
-          Xb[(tl ^ cl) + 16 * c1 + 256 * c2] = old[bi][co][e] + a[mf][bi][co][e];
+          Sb[(tl ^ cl) + 16 * c1 + 256 * c2] = a[mf][bi][co][e];
         }
-  }
 }
 
-__device__ __forceinline__ void scatter_add(double* Xs, const double (&a)[2][4][2][2], int tau, int q0, int q1,
-                                            int wq, int lane) {
-  double* X = Xs + tau * XT_DBL;
+// X_tau += (permuted W_h) for one group of four warps:
+//   registers -> staging tile (permuted) -> group barrier -> every thread adds the 32 elements
+//   that live in its TMEM lane (tcgen05.ld, DADD, tcgen05.st).
+// The staging read-back is conflict-free: lanes 0-15 / 16-31 of a warp read 16 consecutive
+// doubles each.
+__device__ __forceinline__ void scatter_add(double* stg, uint32_t tmem_lane_base, const double (&a)[2][4][2][2],
+                                            int tau, int q0, int q1, int grp, int wq, int lane) {
   switch (q0 * 3 + q1) {
-    case 1: scatter_add_q<0, 1, 2>(X, a, wq, lane); break;
-    case 2: scatter_add_q<0, 2, 1>(X, a, wq, lane); break;
-    case 3: scatter_add_q<1, 0, 2>(X, a, wq, lane); break;
-    case 5: scatter_add_q<1, 2, 0>(X, a, wq, lane); break;
-    case 6: scatter_add_q<2, 0, 1>(X, a, wq, lane); break;
-    default: scatter_add_q<2, 1, 0>(X, a, wq, lane); break;
+    case 1: stage_store_q<0, 1, 2>(stg, a, wq, lane); break;
+    case 2: stage_store_q<0, 2, 1>(stg, a, wq, lane); break;
+    case 3: stage_store_q<1, 0, 2>(stg, a, wq, lane); break;
+    case 5: stage_store_q<1, 2, 0>(stg, a, wq, lane); break;
+    case 6: stage_store_q<2, 0, 1>(stg, a, wq, lane); break;
+    default: stage_store_q<2, 1, 0>(stg, a, wq, lane); break;
   }
+  group_barrier(grp);
+  tmem_fence_after();
+  // owned elements: n = L + 128 d, L = 32 wq + lane  ->  x0 = L & 15, x1 = (L >> 4) + 8 (d & 1), x2 = d >> 1
+  const int x0 = lane & 15, x1lo = 2 * wq + (lane >> 4);
+  const uint32_t tcol = tmem_lane_base + (uint32_t)(tau * TMEM_COLS_PER_TILE);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tcol + 32 * c, r);
+    double sv[16];
+#pragma unroll
+    for (int dd = 0; dd < 16; ++dd) {
+      const int d = 16 * c + dd;
+      sv[dd] = stg[xt_index(x0, x1lo + 8 * (d & 1), d >> 1)];
+    }
+    tmem_wait_ld();
+#pragma unroll
+    for (int dd = 0; dd < 16; ++dd) {
+      const double x = __hiloint2double((int)r[2 * dd + 1], (int)r[2 * dd]) + sv[dd];
+      r[2 * dd] = (uint32_t)__double2loint(x);
+      r[2 * dd + 1] = (uint32_t)__double2hiint(x);
+    }
+    tmem_st32(tcol + 32 * c, r);
+  }
+  tmem_wait_st();
+  tmem_fence_before();
 }
 
 // staging values of one X tile of the epilogue (singles-term operands + eigenvalues) into
@@ -454,23 +514,35 @@ __device__ __forceinline__ void epi_stage_load(const FusedParams& p, const PtCla
   }
 }
 
-__device__ __forceinline__ void carve_smem(unsigned char* raw, double*& Xs, double*& ring, double*& Qs,
-                                           double*& tv, double*& red, uint64_t*& bars) {
+// shared memory: [ring: NSTAGE stages][staging: one 16^3 tile per consumer group][Qs][tv][red]
+// [mbarriers: full[NSTAGE], empty[NSTAGE], go][tmem base].  In the epilogue the six X tiles
+// (6 x 4096 doubles) are copied from TMEM to the start of the buffer, over the drained ring
+// and the first part of the staging tiles.
+constexpr int RING_DBL = NSTAGE * STAGE_DBL;
+constexpr int STG_DBL = 2 * XT_DBL;
+static_assert(RING_DBL + STG_DBL >= 6 * XT_DBL, "epilogue X copy must fit into ring + staging");
+__device__ __forceinline__ void carve_smem(unsigned char* raw, double*& Xs, double*& ring, double*& stg,
+                                           double*& Qs, double*& tv, double*& red, uint64_t*& bars,
+                                           uint32_t*& tmem_slot) {
   Xs = reinterpret_cast<double*>(raw);
-  ring = Xs + 6 * XT_DBL;
-  Qs = ring + NSTAGE * STAGE_DBL;
+  ring = Xs;
+  stg = ring + RING_DBL;
+  Qs = stg + STG_DBL;
   tv = Qs + 3 * 256;
   red = tv + 96;
   bars = reinterpret_cast<uint64_t*>(red + 8);
+  tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 1);
 }
-constexpr int FUSED_SMEM_BYTES = (6 * XT_DBL + NSTAGE * STAGE_DBL + 3 * 256 + 96 + 8) * 8 + 2 * NSTAGE * 8;
+constexpr int FUSED_SMEM_BYTES = (RING_DBL + STG_DBL + 3 * 256 + 96 + 8) * 8 + (2 * NSTAGE + 1) * 8 + 16;
+static_assert(FUSED_SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // ------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *Xs, *ring, *Qs, *tv, *red;
+  double *Xs, *ring, *stg, *Qs, *tv, *red;
   uint64_t* bars;
-  carve_smem(smem_raw, Xs, ring, Qs, tv, red, bars);
+  uint32_t* tmem_slot;
+  carve_smem(smem_raw, Xs, ring, stg, Qs, tv, red, bars, tmem_slot);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nk4 = p.d.nk4, nl4 = p.d.nl4, v = p.d.v, o = p.d.o;
@@ -480,11 +552,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       mbar_init(smem_u32(bars + s), 1);
       mbar_init(smem_u32(bars + NSTAGE + s), NCONSUMER_WARPS);
     }
+    mbar_init(smem_u32(bars + 2 * NSTAGE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp < NCONSUMER_WARPS)
-    for (int idx = tid; idx < 6 * XT_DBL; idx += NCONSUMER_WARPS * 32) Xs[idx] = 0.0;
+  if (warp == 0) {
+    // the whole tensor memory of the SM (one CTA per SM): 6 X tiles use 384 of the 512 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tmem_fence_before();
   __syncthreads();
+  tmem_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
   Pipe pp;
   pp.ring = smem_u32(ring);
@@ -492,16 +573,31 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   pp.empty = smem_u32(bars + NSTAGE);
   pp.slot = 0;
   pp.phase = 0;
+  const uint32_t go_bar = smem_u32(bars + 2 * NSTAGE);
 
   if (warp == NCONSUMER_WARPS) {
     // ===== producer warp =====
-    producer_loop(p, pp, blockIdx.x, gridDim.x);
+    producer_loop(p, pp, go_bar, blockIdx.x, gridDim.x);
     return;
   }
 
   // ===== consumer warps =====
   const int grp = warp >> 2, wq = warp & 3;
-  // without CTA barriers between steps, two read-modify-writes of one X element by different
+  const uint32_t tmem_lane_base = tmem_base + ((uint32_t)(32 * wq) << 16);
+  double* my_stg = stg + grp * XT_DBL;
+  // the two warps that share a TMEM lane quadrant (w, w+4) split the 64 columns of a tile
+  const uint32_t my_cols = 32 * grp;
+  {
+    uint32_t z[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) z[n] = 0u;
+    for (int tau = 0; tau < 6; ++tau) tmem_st32(tmem_lane_base + tau * TMEM_COLS_PER_TILE + my_cols, z);
+    tmem_wait_st();
+    tmem_fence_before();
+    consumer_barrier();
+    tmem_fence_after();
+  }
+  // without CTA barriers between steps, accesses of one X element / staging word by different
   // warps are ordered through the stage ring (a warp can run at most NSTAGE stages ahead of
   // the slowest one); that needs steps of more than NSTAGE stages
   const bool step_sync_always = (nk4 + 2 * nl4) < 2 * NSTAGE;
@@ -522,13 +618,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       // ranges; only then (or for very short steps) are the two scatters separated by barriers
       const bool sync = step_sync_always || (st.h[0].en && st.h[1].en && st.h[0].tau == st.h[1].tau);
       if (!sync) {
-        if (hf.en) scatter_add(Xs, acc, hf.tau, hf.q0, hf.q1, wq, lane);
+        if (hf.en) scatter_add(my_stg, tmem_lane_base, acc, hf.tau, hf.q0, hf.q1, grp, wq, lane);
       } else {
-        if (grp == 0 && hf.en) scatter_add(Xs, acc, hf.tau, hf.q0, hf.q1, wq, lane);
+        if (grp == 0 && hf.en) scatter_add(my_stg, tmem_lane_base, acc, hf.tau, hf.q0, hf.q1, grp, wq, lane);
+        tmem_fence_before();
         consumer_barrier();
-        if (grp == 1 && hf.en) scatter_add(Xs, acc, hf.tau, hf.q0, hf.q1, wq, lane);
+        tmem_fence_after();
+        if (grp == 1 && hf.en) scatter_add(my_stg, tmem_lane_base, acc, hf.tau, hf.q0, hf.q1, grp, wq, lane);
+        tmem_fence_before();
         consumer_barrier();
+        tmem_fence_after();
       }
+    }
+
+    // ---- X tiles: TMEM -> shared memory (over the drained ring), and clear them for the next item
+    tmem_fence_before();
+    consumer_barrier();  // all scatters of the item are done, every ring stage has been consumed
+    tmem_fence_after();
+    {
+      const int x0 = lane & 15, x1lo = 2 * wq + (lane >> 4);
+      for (int tau = 0; tau < tab.ntiles; ++tau) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_lane_base + tau * TMEM_COLS_PER_TILE + my_cols;
+        tmem_ld32(taddr, r);
+        tmem_wait_ld();
+        double* Xt = Xs + tau * XT_DBL;
+#pragma unroll
+        for (int dd = 0; dd < 16; ++dd) {
+          const int d = 16 * grp + dd;
+          Xt[xt_index(x0, x1lo + 8 * (d & 1), d >> 1)] = __hiloint2double((int)r[2 * dd + 1], (int)r[2 * dd]);
+        }
+#pragma unroll
+        for (int n = 0; n < 32; ++n) r[n] = 0u;
+        tmem_st32(taddr, r);
+      }
+      tmem_wait_st();
     }
 
     // ---- epilogue: E_item = sum_tiles sum_x (Xd + Sd)[x] * (sum_nu c_nu Xd[x o nu]) / D[x]
@@ -539,7 +663,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
     // registers one tile ahead so that the global-load latency hides behind the point loop
     double sq0, sq1, sq2, stv0 = 0.0, stv1 = 0.0;
     epi_stage_load(p, tab, ob, 0, hi, hj, hk, pm, tid, sq0, sq1, sq2, stv0, stv1);
-    consumer_barrier();  // all scatters of the item are done
+    // (the barrier that publishes Xs is the first one inside the tile loop)
     for (int tl = 0; tl < tab.ntiles; ++tl) {
       const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
       const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
@@ -587,24 +711,30 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) e_acc += __shfl_down_sync(0xffffffffu, e_acc, off);
     if (lane == 0) red[warp] = e_acc;
-    for (int idx = tid; idx < 6 * XT_DBL; idx += NCONSUMER_WARPS * 32) Xs[idx] = 0.0;
+    tmem_fence_before();
     consumer_barrier();
+    tmem_fence_after();
     if (tid == 0) {
+      mbar_arrive(go_bar);  // Xs has been read by everyone: the producer may refill the ring
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < NCONSUMER_WARPS; ++w) s += red[w];
       atomicAdd(p.e_triple + t, s);
     }
   }
+  consumer_barrier();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
 
 // ------------------------------------------------ debug: one W tile via the main loop
 __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const FusedParams p, WTileJob job,
                                                                     double* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double *Xs, *ring, *Qs, *tv, *red;
+  double *Xs, *ring, *stg, *Qs, *tv, *red;
   uint64_t* bars;
-  carve_smem(smem_raw, Xs, ring, Qs, tv, red, bars);
+  uint32_t* tmem_slot;
+  carve_smem(smem_raw, Xs, ring, stg, Qs, tv, red, bars, tmem_slot);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
