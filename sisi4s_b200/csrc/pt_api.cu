@@ -44,7 +44,7 @@ struct PtHandle_ {
   int keep_raw = 0;
   int grid = 0;
   int order = 1;
-  int prefetch = 12;
+  int debug = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // raw device tensors
@@ -206,9 +206,8 @@ int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "grid")) {
     if (value < 0) return fail(PT_ERR_INVALID, "grid %lld", (long long)value);
     h->grid = (int)value;
-  } else if (!strcmp(key, "prefetch")) {
-    if (value < 0 || value > 4096) return fail(PT_ERR_INVALID, "prefetch %lld", (long long)value);
-    h->prefetch = (int)value;
+  } else if (!strcmp(key, "debug")) {
+    h->debug = (int)value;
   } else if (!strcmp(key, "order")) {
     if (value != 0 && value != 1) return fail(PT_ERR_INVALID, "order %lld", (long long)value);
     h->order = (int)value;
@@ -446,7 +445,7 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
       p.triples = d_list;
       p.ntriples = (int)list.size();
       p.order = h->order;
-      p.prefetch = h->prefetch;
+      p.debug = h->debug;
       p.nitems = (long long)list.size() * h->norbits;
       p.e_triple = d_e;
       int grid = h->grid > 0 ? h->grid : h->sm_count;

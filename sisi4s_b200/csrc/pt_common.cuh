@@ -33,7 +33,8 @@ constexpr int STAGE_DBL = 1152;            // doubles per pipeline stage (9216 B
 constexpr int NSTAGE = 16;              // operand ring depth (X tiles live in TMEM, so the ring owns the smem)
 constexpr int XT_DBL = TILE * TILE * TILE; // one X tile
 constexpr int NCONSUMER_WARPS = 8;
-constexpr int FUSED_THREADS = (NCONSUMER_WARPS + 1) * 32;
+constexpr int NPRODUCER_WARPS = 4;          // stage j of the operand stream is issued by producer warp j % 4
+constexpr int FUSED_THREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
 
 struct Dims {
   int o, v;
@@ -88,7 +89,7 @@ struct FusedParams {
   int norbits;
   int ntriples;
   int order;              // 0: triple-major (orbit fastest), 1: orbit-major (triple fastest; L2 reuse of PPPH tiles)
-  int prefetch;           // L2 prefetch distance of the producer warp in stages (0 = off)
+  int debug;              // measurement switches: 1 = consumers skip LDS/DMMA (operand-feed ceiling), 2 = skip hole stages' DMMA only
   long long nitems;       // ntriples * norbits
   double* e_triple;       // [ntriples], accumulated with atomicAdd
 };

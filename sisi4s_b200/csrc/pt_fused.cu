@@ -174,10 +174,6 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
 // Stage j of a step: j < nk4 is particle chunk j (one 8 KB slab-tile chunk + the enabled
 // 512 B T2 panels), otherwise hole sub-stage lg = j - nk4 (per enabled half one 4 KB T2h
 // chunk + one 512 B HHHP panel chunk).
@@ -201,26 +197,6 @@ __device__ __forceinline__ void issue_stage(const StepSrc& s, int j, int nk4, ui
     }
   }
 }
-// L2 prefetch of the operands of stage j (the small panels in 4 KB pieces every 8th stage)
-__device__ __forceinline__ void prefetch_stage(const StepSrc& s, int j, int nk4, int nl4) {
-  if (j < nk4) {
-    prefetch_l2(s.v + (size_t)j * 1024, 8192u);
-    if ((j & 7) == 0) {
-      const uint32_t bytes = (uint32_t)min(8, nk4 - j) * 512u;
-      if (s.en[0]) prefetch_l2(s.t[0] + (size_t)j * 64, bytes);
-      if (s.en[1]) prefetch_l2(s.t[1] + (size_t)j * 64, bytes);
-    }
-  } else {
-    const int lg = j - nk4;
-    if (s.en[0]) prefetch_l2(s.hh[0] + (size_t)lg * 512, 4096u);
-    if (s.en[1]) prefetch_l2(s.hh[1] + (size_t)lg * 512, 4096u);
-    if (lg == 0) {
-      if (s.en[0]) prefetch_l2(s.u[0], (uint32_t)nl4 * 512u);
-      if (s.en[1]) prefetch_l2(s.u[1], (uint32_t)nl4 * 512u);
-    }
-  }
-}
-
 // Position in the CTA's stream of operand stages (item -> step -> stage); warp-uniform.
 struct StageIter {
   long long item;
@@ -244,52 +220,52 @@ struct StageIter {
     j = 0;
     src = make_step_src(p, c_tab[tc][oc].steps[0], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
   }
-  __device__ __forceinline__ void next(const FusedParams& p, int nst, int stride) {
-    if (++j < nst) return;
-    j = 0;
-    if (++s < nsteps) {
-      src = make_step_src(p, c_tab[tc][oc].steps[s], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
-      return;
+  // move n stages forward in the stream
+  __device__ __forceinline__ void advance(const FusedParams& p, int n, int nst, int stride) {
+    j += n;
+    while (valid && j >= nst) {
+      const int jj = j - nst;
+      if (++s < nsteps) {
+        src = make_step_src(p, c_tab[tc][oc].steps[s], tr.x, tr.y, tr.z, ob.x, ob.y, ob.z);
+      } else {
+        item += stride;
+        load_item(p);
+      }
+      j = jj;
     }
-    item += stride;
-    load_item(p);
   }
 };
 
 
-// producer warp: all 32 lanes run the (uniform) stream bookkeeping, one elected lane
-// issues the copies.  A second iterator runs p.prefetch stages ahead and pulls the same
-// operands into L2, so that an HBM miss never sits on the 3-stage ring's critical path.
-__device__ __forceinline__ void producer_loop(const FusedParams& p, Pipe& pp, uint32_t go_bar, long long first_item,
-                                              int stride) {
-  const int nk4 = p.d.nk4, nl4 = p.d.nl4, nst = nk4 + 2 * nl4;
-  StageIter ld, pf;
+// Producer warps.  One thread's issue rate (mbarrier wait + expect_tx + three or four bulk
+// copies + stream bookkeeping, ~500 clk per stage) cannot feed the DMMA pipe, so
+// NPRODUCER_WARPS warps share the stream: warp pw issues the stages n = pw (mod NPRODUCER_WARPS)
+// of the CTA's global stage sequence.  All 32 lanes run the (uniform) bookkeeping, one elected
+// lane issues the copies.
+__device__ __forceinline__ void producer_loop(const FusedParams& p, const Pipe& pp0, uint32_t go_bar, int pw,
+                                              long long first_item, int stride) {
+  const int nk4 = p.d.nk4, nst = nk4 + 2 * p.d.nl4;
+  StageIter ld;
   ld.item = first_item;
   ld.load_item(p);
-  pf = ld;
+  if (ld.valid) ld.advance(p, pw, nst, stride);
   const bool leader = elect_one();
-  const int pfd = p.prefetch;  // L2 prefetch distance in stages (0 = off)
-  if (pfd == 0) pf.valid = false;
-  for (int n = 0; n < pfd && pf.valid; ++n) {
-    if (leader) prefetch_stage(pf.src, pf.j, nk4, nl4);
-    pf.next(p, nst, stride);
-  }
+  uint32_t n = (uint32_t)pw;  // global stage number -> ring slot n % NSTAGE, phase (n / NSTAGE) & 1
   uint32_t items_started = 0;
+  long long cur_item = -1;
   while (ld.valid) {
-    if (ld.s == 0 && ld.j == 0) {
+    if (ld.item != cur_item) {
       // the epilogue of the previous item copies the X tiles over the ring: wait until it is done
       if (items_started > 0) mbar_wait(go_bar, (items_started - 1) & 1);
       ++items_started;
+      cur_item = ld.item;
     }
-    if (pf.valid) {
-      if (leader) prefetch_stage(pf.src, pf.j, nk4, nl4);
-      pf.next(p, nst, stride);
-    }
-    const uint32_t full = pp.full + 8 * pp.slot, stage = pp.ring + pp.slot * (STAGE_DBL * 8);
-    mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
+    const uint32_t slot = n % NSTAGE, phase = (n / NSTAGE) & 1;
+    const uint32_t full = pp0.full + 8 * slot, stage = pp0.ring + slot * (STAGE_DBL * 8);
+    mbar_wait(pp0.empty + 8 * slot, phase ^ 1);
     if (leader) issue_stage(ld.src, ld.j, nk4, stage, full);
-    pp.advance();
-    ld.next(p, nst, stride);
+    n += NPRODUCER_WARPS;
+    ld.advance(p, NPRODUCER_WARPS, nst, stride);
   }
 }
 
@@ -575,9 +551,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   pp.phase = 0;
   const uint32_t go_bar = smem_u32(bars + 2 * NSTAGE);
 
-  if (warp == NCONSUMER_WARPS) {
-    // ===== producer warp =====
-    producer_loop(p, pp, go_bar, blockIdx.x, gridDim.x);
+  if (warp >= NCONSUMER_WARPS) {
+    // ===== producer warps =====
+    producer_loop(p, pp, go_bar, warp - NCONSUMER_WARPS, blockIdx.x, gridDim.x);
     return;
   }
 
@@ -613,7 +589,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       const PtStep& st = tab.steps[s];
       const PtHalf& hf = st.h[grp];
       double acc[2][4][2][2];
-      consume_step(acc, ring, pp, nk4, nl4, hf.en, grp, wq, lane);
+      consume_step(acc, ring, pp, nk4, nl4, (p.debug & 1) ? 0 : hf.en, grp, wq, lane);
       // the halves of a step target different X tiles except in orbits with coinciding
       // ranges; only then (or for very short steps) are the two scatters separated by barriers
       const bool sync = step_sync_always || (st.h[0].en && st.h[1].en && st.h[0].tau == st.h[1].tau);
@@ -757,6 +733,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
   src.u[0] = src.u[1] = p.Ut + ut_panel_off(p.d, job.y, job.z, job.R);
   src.en[0] = 1;
   src.en[1] = 0;
+  if (warp > NCONSUMER_WARPS) return;
   if (warp == NCONSUMER_WARPS) {
     const bool leader = elect_one();
     const int nst = p.d.nk4 + 2 * p.d.nl4;
