@@ -206,6 +206,7 @@ def main():
     import torch.distributed as dist
     from sisi4s_b200 import synthetic as S
     from sisi4s_b200.triples import TriplesEngine, CcsdPerturbativeTriples
+    from sisi4s_b200.sharding import TripleShards
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the (T) path has no CPU fallback "
@@ -220,11 +221,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    shards = TripleShards(O_, world, rank)
+
     def allreduce(x, op):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=op)
-        return float(t.item())
+        return shards.max(x, dev) if op is dist.ReduceOp.MAX else shards.sum(x, dev)
 
     # ---- setup (untimed): inputs, FP64 ceiling, upload + pack
     t_setup = time.time()
@@ -236,7 +236,7 @@ def main():
     t_setup = time.time() - t_setup
 
     def step_range(s):
-        return eng.partition(NBATCH * world, (s % NBATCH) * world + rank)
+        return shards.my_range(NBATCH, s)
 
     for s in range(args.warmup):
         eng.run(*step_range(s))
@@ -256,11 +256,11 @@ def main():
     wall = time.time() - wall0
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.stats().kernel_launches - launches0
-    t_max = allreduce(dev_s, dist.ReduceOp.MAX if world > 1 else None)
-    k_max = allreduce(ker_s, dist.ReduceOp.MAX if world > 1 else None)
-    fl_all = allreduce(fl, dist.ReduceOp.SUM if world > 1 else None)
-    e_all = allreduce(e_sum, dist.ReduceOp.SUM if world > 1 else None)   # the one data collective
-    launches_all = int(allreduce(float(launches), dist.ReduceOp.SUM if world > 1 else None))
+    t_max = allreduce(dev_s, dist.ReduceOp.MAX)
+    k_max = allreduce(ker_s, dist.ReduceOp.MAX)
+    fl_all = allreduce(fl, dist.ReduceOp.SUM)
+    e_all = allreduce(e_sum, dist.ReduceOp.SUM)   # the one data collective
+    launches_all = int(allreduce(float(launches), dist.ReduceOp.SUM))
     value = fl_all / t_max * 1e-12
     eng.close()
 
@@ -283,7 +283,7 @@ def main():
             """the plugin run() restricted to this rank's share of the sorted triples"""
             def run(self):
                 with self.make_engine() as en:
-                    r = en.run(*en.partition(world, rank))
+                    r = en.run(*shards.my_range())
                     self.stats = en.stats()
                 return r
 
@@ -291,9 +291,9 @@ def main():
         w0 = time.time()
         alg = Shard(argsmap, data)
         r = alg.run()
-        e_e2e = allreduce(r.energy, dist.ReduceOp.SUM if world > 1 else None)
+        e_e2e = allreduce(r.energy, dist.ReduceOp.SUM)
         barrier()
-        w_e2e = allreduce(time.time() - w0, dist.ReduceOp.MAX if world > 1 else None)
+        w_e2e = allreduce(time.time() - w0, dist.ReduceOp.MAX)
         fl_e2e = flops_of(O_, V_, int(weights.sum()))
         e2e = {"value": fl_e2e / w_e2e * 1e-12, "unit": "TFLOP/s", "seconds": w_e2e,
                "h2d_bytes_per_step": float(alg.stats.bytes_h2d), "d2h_bytes_per_step": float(alg.stats.bytes_d2h),

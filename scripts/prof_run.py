@@ -5,12 +5,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sisi4s_b200 import synthetic as S
 from sisi4s_b200.triples import TriplesEngine
 
-b = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+# "step P" = the bench's step P (partition P of 8); otherwise <first triple> <count>
+step = len(sys.argv) > 1 and sys.argv[1] == "step"
+b = 5000 if step or len(sys.argv) <= 1 else int(sys.argv[1])
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 order = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
 with TriplesEngine(40, 300) as eng:
     eng.set_inputs(*inp.args())
     eng.set_option("order", order)
-    r = eng.run(b, b + n)
+    rng = eng.partition(8, n) if step else (b, b + n)
+    r = eng.run(*rng)
     print("E", r.energy, "s_kernel", r.seconds_kernel, "TF/s", r.flops / r.seconds_kernel * 1e-12)
