@@ -60,6 +60,7 @@ typedef struct PtStats {
   int64_t triples_run;       /* sorted triples processed by the last pt_run            */
   int32_t sm_count;
   int32_t reserved;
+  int64_t slab_loads;        /* PPPH slabs (re)built or re-uploaded on demand (slab_slots < o) */
 } PtStats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -72,7 +73,13 @@ const char *pt_version(void);
 
 /* options: "engine" (PtEngine), "keep_raw" (0/1: keep unpacked copies on the
  * device, required by PT_ENGINE_NAIVE and the debug entry points; set BEFORE
- * the tensors), "grid" (CTAs of the fused kernel, 0 = one per SM).          */
+ * the tensors), "grid" (CTAs of the fused kernel, 0 = one per SM),
+ * "slab_slots" (S: hole-blocked residency of the PPPH integrals -- only S >= 3
+ * of the o slabs V[:,:,:,k] are resident at a time, for shapes whose v^3 o
+ * tensor exceeds HBM (BASELINE configs[4]); pt_run then walks the sorted
+ * triples by hole blocks of width S/3 and (re)builds slabs on demand from the
+ * resident vertex or re-uploads them from the pt_set_ppph_host tensor; 0 = all
+ * resident; set BEFORE the PPPH integrals / vertex).                          */
 int pt_set_option(pt_handle_t h, const char *key, int64_t value);
 
 /* ---- inputs (names = the reference's YAML argument keys) ------------------ */
@@ -92,10 +99,17 @@ int pt_set_hhhp(pt_handle_t h, const double *vijka);
  * with disjoint ranges so the caller never holds more than a few slabs
  * (PerturbativeTriples.cxx:176,190).                                          */
 int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double *slab);
+/* The whole PPPHCoulombIntegrals[v,v,v,o] tensor in caller-owned HOST memory.
+ * Without slab_slots it is uploaded at once (= pt_set_ppph_slabs(h,0,o,..)).
+ * With slab_slots < o only the pointer is recorded: it must stay valid until
+ * pt_destroy, and pt_run uploads the slabs its current hole blocks need.       */
+int pt_set_ppph_host(pt_handle_t h, const double *vabci);
 /* Alternative to pt_set_ppph_slabs: CoulombVertex Gamma[NF,Np,Np] complex,
  * given as separate real and imaginary parts (fromComplexTensor,
  * CcsdPerturbativeTriples.cxx:48-78).  PPPH is built on the device exactly as
- * CoulombIntegralsFromVertex.cxx:430-431; particles are the last v states.   */
+ * CoulombIntegralsFromVertex.cxx:430-431; particles are the last v states.
+ * With slab_slots < o the vertex stays resident on the device and slabs are
+ * rebuilt when needed, like the reference does per triple (:89-92).           */
 int pt_set_vertex(pt_handle_t h, int nf, int np, const double *gamma_re, const double *gamma_im);
 
 /* ---- run ------------------------------------------------------------------ */

@@ -8,7 +8,7 @@ inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
 with TriplesEngine(40, 300) as eng:
     eng.set_inputs(*inp.args())
     b, e = eng.partition(8, 3)
-    for dbg in (0, 1, 0, 1):
+    for dbg in (0, 1):
         eng.set_option("debug", dbg)
         r = eng.run(b, e)
         print("debug", dbg, "s_kernel", r.seconds_kernel, "equiv TF/s", r.flops / r.seconds_kernel * 1e-12, flush=True)

@@ -29,6 +29,7 @@ class PtStats(C.Structure):
         ("triples_run", C.c_int64),
         ("sm_count", C.c_int32),
         ("reserved", C.c_int32),
+        ("slab_loads", C.c_int64),
     ]
 
 
@@ -47,6 +48,7 @@ SYMBOLS = {
     "pt_set_pphh": (C.c_int, [_H, _DP]),
     "pt_set_hhhp": (C.c_int, [_H, _DP]),
     "pt_set_ppph_slabs": (C.c_int, [_H, C.c_int, C.c_int, _DP]),
+    "pt_set_ppph_host": (C.c_int, [_H, _DP]),
     "pt_set_vertex": (C.c_int, [_H, C.c_int, C.c_int, _DP, _DP]),
     "pt_num_triples": (C.c_int64, [C.c_int]),
     "pt_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

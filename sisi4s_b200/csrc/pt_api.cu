@@ -53,7 +53,20 @@ struct PtHandle_ {
   // packed
   double *Tt = nullptr, *T2h = nullptr, *Vt = nullptr, *Ut = nullptr;
   double* slab_stage = nullptr;  // one raw PPPH slab
-  std::vector<char> slab_set;
+  std::vector<char> slab_set;    // a source for slab k has been given
+  // hole-blocked PPPH residency (option slab_slots = S < o): Vt holds S slab slots, slabs are
+  // (re)built on demand from a resident vertex or a caller-owned host tensor
+  int slab_slots = 0;
+  std::vector<int> slot_of;      // hole -> slot of its packed slab, -1 = not resident
+  std::vector<int> hole_in;      // slot -> hole, -1 = free
+  std::vector<long long> slot_tick;
+  long long tick = 0;
+  int* d_vslot = nullptr;
+  double *g_re = nullptr, *g_im = nullptr;  // resident CoulombVertex parts (blocked mode)
+  int g_nf = 0, g_np = 0;
+  const double* host_ppph = nullptr;        // caller-owned PPPHCoulombIntegrals[v,v,v,o]
+  int nslots() const { return (slab_slots > 0 && slab_slots < d.o) ? slab_slots : d.o; }
+  bool blocked() const { return nslots() < d.o; }
   bool have_eps = false, have_t1 = false, have_t2 = false, have_pphh = false, have_hhhp = false;
   // work lists
   uchar4* d_orbits = nullptr;
@@ -158,6 +171,7 @@ int pt_create(pt_handle_t* out, int o, int v, int device) {
   h->sm_count = prop.multiProcessorCount;
   h->stats.sm_count = prop.multiProcessorCount;
   h->slab_set.assign(o, 0);
+  h->slot_of.assign(o, -1);
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
@@ -185,10 +199,11 @@ int pt_destroy(pt_handle_t h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   double* ptrs[] = {h->epsi, h->epsa, h->t1, h->pphh, h->t2_raw, h->hhhp_raw, h->ppph_raw,
-                    h->Tt, h->T2h, h->Vt, h->Ut, h->slab_stage};
+                    h->Tt, h->T2h, h->Vt, h->Ut, h->slab_stage, h->g_re, h->g_im};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   if (h->d_orbits) cudaFree(h->d_orbits);
+  if (h->d_vslot) cudaFree(h->d_vslot);
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
@@ -206,6 +221,10 @@ int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
   } else if (!strcmp(key, "grid")) {
     if (value < 0) return fail(PT_ERR_INVALID, "grid %lld", (long long)value);
     h->grid = (int)value;
+  } else if (!strcmp(key, "slab_slots")) {
+    if (value < 0 || (value > 0 && value < 3)) return fail(PT_ERR_INVALID, "slab_slots %lld (0 = all resident, else >= 3)", (long long)value);
+    if (h->Vt) return fail(PT_ERR_INVALID, "slab_slots must be set before the PPPH integrals / vertex");
+    h->slab_slots = (int)value;
   } else if (!strcmp(key, "debug")) {
     h->debug = (int)value;
   } else if (!strcmp(key, "order")) {
@@ -298,15 +317,35 @@ int pt_set_hhhp(pt_handle_t h, const double* vijka) {
 
 static int ensure_ppph_buffers(pt_handle_t h) {
   const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
-  if (!h->Vt) CU(h->alloc(&h->Vt, vt_elems(h->d)));
+  if (h->blocked() && h->keep_raw) return fail(PT_ERR_INVALID, "slab_slots and keep_raw are mutually exclusive");
+  if (!h->Vt) {
+    CU(h->alloc(&h->Vt, vt_slab_elems(h->d) * (size_t)h->nslots()));
+    h->hole_in.assign(h->nslots(), -1);
+    h->slot_tick.assign(h->nslots(), 0);
+  }
   if (!h->slab_stage) CU(h->alloc(&h->slab_stage, slab));
   if (h->keep_raw && !h->ppph_raw) CU(h->alloc(&h->ppph_raw, slab * h->d.o));
+  if (h->blocked() && !h->d_vslot) CU(h->alloc(&h->d_vslot, (size_t)h->d.o));
+  return PT_OK;
+}
+
+// pack the raw slab `src` (device) of hole k into slot `slot`
+static int pack_into_slot(pt_handle_t h, const double* src, int k, int slot) {
+  CU(launch_pack_vt_slab(src, h->Vt + vt_slab_elems(h->d) * (size_t)slot, h->d, h->stream));
+  h->stats.kernel_launches += 1;
+  if (h->hole_in[slot] >= 0) h->slot_of[h->hole_in[slot]] = -1;
+  h->hole_in[slot] = k;
+  h->slot_of[k] = slot;
+  h->slot_tick[slot] = ++h->tick;
   return PT_OK;
 }
 
 int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
   if (!h || !slabs) return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: null");
   if (k0 < 0 || k1 > h->d.o || k0 >= k1) return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: range [%d,%d) of %d", k0, k1, h->d.o);
+  if (h->blocked())
+    return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: with slab_slots < o the slabs are fetched on demand; "
+                                "use pt_set_ppph_host or pt_set_vertex");
   CU(cudaSetDevice(h->device));
   if (int rc = ensure_ppph_buffers(h)) return rc;
   Timer tm(h->ev0, h->ev1, h->stream);
@@ -314,11 +353,22 @@ int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
   for (int k = k0; k < k1; ++k) {
     double* dst = h->keep_raw ? h->ppph_raw + slab * k : h->slab_stage;
     if (int rc = upload(h, dst, slabs + slab * (size_t)(k - k0), slab)) return rc;
-    CU(launch_pack_vt_slab(dst, h->Vt + vt_slab_elems(h->d) * k, h->d, h->stream));
-    h->stats.kernel_launches += 1;
+    if (int rc = pack_into_slot(h, dst, k, k)) return rc;
     h->slab_set[k] = 1;
   }
   h->stats.seconds_upload += tm.stop();
+  return PT_OK;
+}
+
+int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
+  if (!h || !vabci) return fail(PT_ERR_INVALID, "pt_set_ppph_host: null");
+  if (!h->blocked()) return pt_set_ppph_slabs(h, 0, h->d.o, vabci);
+  CU(cudaSetDevice(h->device));
+  if (int rc = ensure_ppph_buffers(h)) return rc;
+  h->host_ppph = vabci;
+  std::fill(h->slab_set.begin(), h->slab_set.end(), 1);
+  std::fill(h->slot_of.begin(), h->slot_of.end(), -1);
+  std::fill(h->hole_in.begin(), h->hole_in.end(), -1);
   return PT_OK;
 }
 
@@ -329,21 +379,67 @@ int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double
   if (int rc = ensure_ppph_buffers(h)) return rc;
   Timer tm(h->ev0, h->ev1, h->stream);
   const size_t n = (size_t)nf * np * np, slab = (size_t)h->d.v * h->d.v * h->d.v;
-  double *dre = nullptr, *dim_ = nullptr;
-  CU(cudaMalloc((void**)&dre, n * sizeof(double)));
-  CU(cudaMalloc((void**)&dim_, n * sizeof(double)));
-  if (int rc = upload(h, dre, gre, n)) return rc;
-  if (int rc = upload(h, dim_, gim, n)) return rc;
+  if (h->g_re) { CU(cudaFree(h->g_re)); h->g_re = nullptr; }
+  if (h->g_im) { CU(cudaFree(h->g_im)); h->g_im = nullptr; }
+  CU(cudaMalloc((void**)&h->g_re, n * sizeof(double)));
+  CU(cudaMalloc((void**)&h->g_im, n * sizeof(double)));
+  h->g_nf = nf; h->g_np = np;
+  if (int rc = upload(h, h->g_re, gre, n)) return rc;
+  if (int rc = upload(h, h->g_im, gim, n)) return rc;
+  if (h->blocked()) {
+    // vertex-direct mode: the vertex stays resident, slabs are built when a launch needs them
+    h->host_ppph = nullptr;
+    h->bytes_alloc += 2.0 * (double)(n * sizeof(double));
+    std::fill(h->slab_set.begin(), h->slab_set.end(), 1);
+    std::fill(h->slot_of.begin(), h->slot_of.end(), -1);
+    std::fill(h->hole_in.begin(), h->hole_in.end(), -1);
+    h->stats.seconds_upload += tm.stop();
+    return PT_OK;
+  }
   for (int k = 0; k < h->d.o; ++k) {
     double* dst = h->keep_raw ? h->ppph_raw + slab * k : h->slab_stage;
-    CU(launch_ppph_slab_from_vertex(dre, dim_, nf, np, k, dst, h->d, h->stream));
-    CU(launch_pack_vt_slab(dst, h->Vt + vt_slab_elems(h->d) * k, h->d, h->stream));
-    h->stats.kernel_launches += 2;
+    CU(launch_ppph_slab_from_vertex(h->g_re, h->g_im, nf, np, k, dst, h->d, h->stream));
+    h->stats.kernel_launches += 1;
+    if (int rc = pack_into_slot(h, dst, k, k)) return rc;
     h->slab_set[k] = 1;
   }
   h->stats.seconds_upload += tm.stop();
-  CU(cudaFree(dre));
-  CU(cudaFree(dim_));
+  CU(cudaFree(h->g_re)); h->g_re = nullptr;
+  CU(cudaFree(h->g_im)); h->g_im = nullptr;
+  return PT_OK;
+}
+
+// blocked mode: make the slabs of all holes in `need` resident (LRU replacement among the slots
+// that hold none of them), then publish the hole -> slot table to the device
+static int ensure_slabs(pt_handle_t h, const std::vector<int>& need) {
+  const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+  std::vector<char> pinned(h->nslots(), 0);
+  for (int z : need)
+    if (h->slot_of[z] >= 0) { pinned[h->slot_of[z]] = 1; h->slot_tick[h->slot_of[z]] = ++h->tick; }
+  for (int z : need) {
+    if (h->slot_of[z] >= 0) continue;
+    int victim = -1;
+    for (int s = 0; s < h->nslots(); ++s) {
+      if (pinned[s]) continue;
+      if (h->hole_in[s] < 0) { victim = s; break; }
+      if (victim < 0 || h->slot_tick[s] < h->slot_tick[victim]) victim = s;
+    }
+    if (victim < 0) return fail(PT_ERR_INVALID, "ensure_slabs: %zu slabs needed, %d slots", need.size(), h->nslots());
+    if (h->g_re) {
+      CU(launch_ppph_slab_from_vertex(h->g_re, h->g_im, h->g_nf, h->g_np, z, h->slab_stage, h->d, h->stream));
+      h->stats.kernel_launches += 1;
+    } else if (h->host_ppph) {
+      if (int rc = upload(h, h->slab_stage, h->host_ppph + slab * (size_t)z, slab)) return rc;
+    } else {
+      return fail(PT_ERR_MISSING, "Missing argument: PPPHCoulombIntegrals (or CoulombVertex)");
+    }
+    if (int rc = pack_into_slot(h, h->slab_stage, z, victim)) return rc;
+    pinned[victim] = 1;
+    h->stats.slab_loads += 1;
+  }
+  // pageable source: the copy is staged before the call returns, and it is ordered on the
+  // stream behind the previous launch that read the table
+  CU(cudaMemcpyAsync(h->d_vslot, h->slot_of.data(), (size_t)h->d.o * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   return PT_OK;
 }
 
@@ -426,49 +522,72 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
   } else {
     // i=j=k triples contribute exactly zero (sum of the spin factors over S3 vanishes), the
     // reference only accumulates rounding noise there (CcsdPerturbativeTriples.cxx:156-158)
-    std::vector<int4> list;
-    std::vector<int> where;
+    struct Entry { int4 t; int where; long long key; };
+    std::vector<Entry> ent;
+    // hole-blocked residency: triples are grouped by the hole blocks (I<=J<=K) of width
+    // b = slots/3 they touch; one launch per group with the <= 3b slabs of those blocks resident
+    const int bw = h->blocked() ? h->nslots() / 3 : h->d.o;
     for (size_t n = 0; n < tr.size(); ++n) {
       const int c = triple_class(tr[n]);
       if (c == 3) continue;
-      list.push_back(make_int4(tr[n].i, tr[n].j, tr[n].k, c));
-      where.push_back((int)n);
+      const long long nb = (h->d.o + bw - 1) / bw;
+      const long long key = h->blocked() ? ((long long)(tr[n].i / bw) * nb + tr[n].j / bw) * nb + tr[n].k / bw : 0;
+      ent.push_back({make_int4(tr[n].i, tr[n].j, tr[n].k, c), (int)n, key});
     }
-    if (!list.empty()) {
+    if (h->blocked())
+      std::stable_sort(ent.begin(), ent.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+    h->stats.seconds_kernel = 0.0;
+    if (!ent.empty()) {
+      std::vector<int4> list(ent.size());
+      for (size_t n = 0; n < ent.size(); ++n) list[n] = ent[n].t;
       int4* d_list = nullptr;
       double* d_e = nullptr;
       CU(cudaMalloc((void**)&d_list, list.size() * sizeof(int4)));
       CU(cudaMalloc((void**)&d_e, list.size() * sizeof(double)));
       CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
       CU(cudaMemsetAsync(d_e, 0, list.size() * sizeof(double), h->stream));
-      FusedParams p = make_params(h);
-      p.triples = d_list;
-      p.ntriples = (int)list.size();
-      p.order = h->order;
-      p.debug = h->debug;
-      p.nitems = (long long)list.size() * h->norbits;
-      p.e_triple = d_e;
-      int grid = h->grid > 0 ? h->grid : h->sm_count;
-      if ((long long)grid > p.nitems) grid = (int)p.nitems;
       cudaEvent_t k0, k1;
       CU(cudaEventCreate(&k0));
       CU(cudaEventCreate(&k1));
-      CU(cudaEventRecord(k0, h->stream));
-      CU(launch_fused(p, grid, h->stream));
-      CU(cudaEventRecord(k1, h->stream));
-      CU(cudaEventSynchronize(k1));
-      float kms = 0;
-      CU(cudaEventElapsedTime(&kms, k0, k1));
-      h->stats.seconds_kernel = kms * 1e-3;
+      for (size_t g0 = 0; g0 < ent.size();) {
+        size_t g1 = g0;
+        while (g1 < ent.size() && ent[g1].key == ent[g0].key) ++g1;
+        FusedParams p = make_params(h);
+        if (h->blocked()) {
+          std::vector<int> need;
+          const int first[3] = {ent[g0].t.x / bw * bw, ent[g0].t.y / bw * bw, ent[g0].t.z / bw * bw};
+          for (int m = 0; m < 3; ++m)
+            for (int z = first[m]; z < std::min(first[m] + bw, h->d.o); ++z)
+              if (std::find(need.begin(), need.end(), z) == need.end()) need.push_back(z);
+          if (int rc = ensure_slabs(h, need)) return rc;
+          p.vslot = h->d_vslot;
+        }
+        p.triples = d_list + g0;
+        p.ntriples = (int)(g1 - g0);
+        p.order = h->order;
+        p.debug = h->debug;
+        p.nitems = (long long)(g1 - g0) * h->norbits;
+        p.e_triple = d_e + g0;
+        int grid = h->grid > 0 ? h->grid : h->sm_count;
+        if ((long long)grid > p.nitems) grid = (int)p.nitems;
+        CU(cudaEventRecord(k0, h->stream));
+        CU(launch_fused(p, grid, h->stream));
+        CU(cudaEventRecord(k1, h->stream));
+        CU(cudaEventSynchronize(k1));
+        float kms = 0;
+        CU(cudaEventElapsedTime(&kms, k0, k1));
+        h->stats.seconds_kernel += kms * 1e-3;
+        h->stats.kernel_launches += 1;
+        g0 = g1;
+      }
       CU(cudaEventDestroy(k0));
       CU(cudaEventDestroy(k1));
-      h->stats.kernel_launches += 1;
       std::vector<double> el(list.size());
       CU(cudaMemcpyAsync(el.data(), d_e, list.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
       h->stats.bytes_h2d += (double)(list.size() * sizeof(int4));
       h->stats.bytes_d2h += (double)(list.size() * sizeof(double));
-      for (size_t n = 0; n < list.size(); ++n) e[where[n]] = el[n];
+      for (size_t n = 0; n < list.size(); ++n) e[ent[n].where] = el[n];
       CU(cudaFree(d_list));
       CU(cudaFree(d_e));
     }

@@ -80,6 +80,7 @@ struct FusedParams {
   const double* T2h;
   const double* Vt;
   const double* Ut;
+  const int* vslot;    // hole z -> slot of its PPPH slab in Vt; nullptr = identity (all slabs resident)
   const double* t1;    // raw [v,o]
   const double* pphh;  // raw [v,v,o,o]
   const double* epsi;

@@ -141,7 +141,8 @@ __device__ __forceinline__ StepSrc make_step_src(const FusedParams& p, const PtS
   const int P = sel3(rg0, rg1, rg2, st.r0);
   const int Q = sel3(rg0, rg1, rg2, st.r1);
   const int R = sel3(rg0, rg1, rg2, st.r2);
-  s.v = p.Vt + vt_tile_off(p.d, z, Q, R);
+  // hole-blocked PPPH residency: slab z lives in slot vslot[z] of Vt (identity when all slabs are resident)
+  s.v = p.Vt + vt_tile_off(p.d, p.vslot ? p.vslot[z] : z, Q, R);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int x = sel3(h0, h1, h2, st.h[h].tx);
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
   pp.slot = 0;
   pp.phase = 0;
   StepSrc src;
-  src.v = p.Vt + vt_tile_off(p.d, job.z, job.Q, job.R);
+  src.v = p.Vt + vt_tile_off(p.d, p.vslot ? p.vslot[job.z] : job.z, job.Q, job.R);
   src.t[0] = src.t[1] = p.Tt + tt_panel_off(p.d, job.x, job.y, job.P);
   src.hh[0] = src.hh[1] = p.T2h + t2h_block_off(p.d, job.x, job.P, job.Q);
   src.u[0] = src.u[1] = p.Ut + ut_panel_off(p.d, job.y, job.z, job.R);

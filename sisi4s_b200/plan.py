@@ -1,0 +1,139 @@
+"""YAML execution plans for the (T) step: the reference's file-format algorithms next to the
+GPU step, so that a plan written for sisi4s (``sisi4s -i in.yaml``; parser: reference
+src/Parser.cxx:22-109, driver: src/Sisi4s.cxx:22-103) runs unchanged as far as it consists of
+readers/writers and the triples step:
+
+    - name: DefineHolesAndParticles   {in: {fileName: EigenEnergies.yaml}, out: {...}}
+    - name: Read                      {in: {fileName: CoulombVertex.yaml}, out: {destination: $CoulombVertex}}
+    - name: TensorReader              {in: {file: T2.bin, mode: binary}, out: {Data: $CcsdDoublesAmplitudes}}
+    - name: CcsdPerturbativeTriples   {in: {...}, out: {CcsdPerturbativeTriplesEnergy: $E}}
+    - name: TensorWriter              {in: {Data: $E}}
+
+    python -m sisi4s_b200 in.yaml        (cwd-relative file names, like the reference)
+
+Algorithms that produce the inputs by computation (Hartree-Fock, integral transformation, the
+CCSD solver) are out of scope; a plan naming one of them fails with the
+reference's behaviour for an unknown algorithm made explicit.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import tensor_io as TIO
+from .triples import Algorithm, AlgorithmFactory, SisiException, register
+
+
+def _data_name(alg: Algorithm, arg: str) -> str:
+    """getArgumentData(arg)->getName() (Algorithm.cxx:57-76): the symbol behind ``$Name``."""
+    if arg not in alg.arguments:
+        raise SisiException(f"Missing argument: {arg}")
+    val = alg.arguments[arg]
+    return val[1:] if isinstance(val, str) and val.startswith("$") else arg
+
+
+def _text(alg: Algorithm, name: str, default=None) -> str:
+    """getTextArgument (Algorithm.cxx:78-97)."""
+    if name not in alg.arguments:
+        if default is None:
+            raise SisiException(f"Missing argument: {name}")
+        return default
+    return str(alg.arguments[name])
+
+
+@register
+class TensorReader(Algorithm):
+    """reference src/algorithms/TensorReader.cxx:14-68 (modes "text" | "binary")."""
+    name = "TensorReader"
+
+    def run(self):
+        name = _data_name(self, "Data")
+        mode = _text(self, "mode", "text")
+        if self.getIntegerArgument("precision", 64) != 64:
+            raise SisiException("TensorReader: only precision 64 is supported")
+        if mode == "binary":
+            a = TIO.read_binary(_text(self, "file", name + ".bin"),
+                                mmap=bool(self.getIntegerArgument("mmap", 0)))
+        else:
+            _, a = TIO.read_text(_text(self, "file", name + ".dat"), _text(self, "delimiter", " "))
+        self.data[name] = a
+
+
+@register
+class ComplexTensorReader(TensorReader):
+    """reference src/algorithms/ComplexTensorReader.cxx: same formats, complex elements."""
+    name = "ComplexTensorReader"
+
+
+@register
+class TensorWriter(Algorithm):
+    """reference src/algorithms/TensorWriter.cxx:20-60."""
+    name = "TensorWriter"
+
+    def run(self):
+        name = _data_name(self, "Data")
+        val = self._resolve("Data")
+        a = np.asarray(val, dtype=np.complex128 if np.iscomplexobj(val) else np.float64)
+        binary = _text(self, "mode", "text") == "binary"
+        path = _text(self, "file", name + (".bin" if binary else ".dat"))
+        if binary:
+            TIO.write_binary(path, a)
+        else:
+            TIO.write_text(path, a, name, _text(self, "rowIndexOrder", ""),
+                           _text(self, "columnIndexOrder", ""), _text(self, "delimiter", " "))
+
+
+@register
+class Read(Algorithm):
+    """reference src/algorithms/Read.cxx:25-104 (cc4s yaml + .elements)."""
+    name = "Read"
+
+    def run(self):
+        self.data[_data_name(self, "destination")] = TIO.read_cc4s(_text(self, "fileName"))
+
+
+@register
+class DefineHolesAndParticles(Algorithm):
+    """reference src/algorithms/cc4s/DefineHolesAndParticles.cxx:8-52."""
+    name = "DefineHolesAndParticles"
+
+    def run(self):
+        holes, particles = TIO.read_eigenenergies(_text(self, "fileName"))
+        self.data[_data_name(self, "HoleEigenEnergies")] = holes
+        self.data[_data_name(self, "ParticleEigenEnergies")] = particles
+
+
+def parse_plan(text: str) -> list[dict]:
+    """Parser::parse (reference src/Parser.cxx:22-109): a YAML sequence of
+    {name, in: {..}, out: {..}} nodes; other keys of a node (anchors on a Nop step) are ignored."""
+    import yaml
+    nodes = yaml.safe_load(text)
+    if not isinstance(nodes, list):
+        raise SisiException("the execution plan must be a YAML sequence of algorithms")
+    plan = []
+    for n in nodes:
+        if not isinstance(n, dict) or "name" not in n:
+            raise SisiException("every step needs a name")
+        if n["name"] == "Nop":
+            continue
+        plan.append({"name": n["name"], "in": n.get("in") or {}, "out": n.get("out") or {}})
+    return plan
+
+
+def run_plan_file(path: str, data: dict | None = None, log=print) -> dict:
+    """Sisi4s::run (reference src/Sisi4s.cxx:22-103) for the supported algorithms."""
+    data = {} if data is None else data
+    with open(path) as f:
+        plan = parse_plan(f.read())
+    for n, node in enumerate(plan):
+        args = dict(node["in"])
+        args.update(node["out"])
+        alg = AlgorithmFactory.create(node["name"], args, data)
+        if alg is None:
+            raise SisiException(f"step {n + 1}: algorithm {node['name']} is not provided by sisi4s_b200 "
+                                f"(available: {sorted(Algorithm.registry)})")
+        log(f"step={n + 1} {node['name']}")
+        alg.run()
+        if getattr(alg, "log", None):
+            for k, v in alg.log.items():
+                log(f"  {k}={v:.15g}")
+    return data

@@ -56,7 +56,7 @@ class TriplesEngine:
     """One GPU's (T) engine: owns a ``pt_handle_t``."""
 
     def __init__(self, o: int, v: int, device: int = 0, engine: int = _lib.PT_ENGINE_FUSED,
-                 keep_raw: bool = False, grid: int = 0):
+                 keep_raw: bool = False, grid: int = 0, slab_slots: int = 0):
         self.lib = _lib.load()
         self.o, self.v = int(o), int(v)
         self._h = C.c_void_p()
@@ -65,6 +65,9 @@ class TriplesEngine:
         self.set_option("engine", int(engine))
         if grid:
             self.set_option("grid", int(grid))
+        if slab_slots:
+            self.set_option("slab_slots", int(slab_slots))
+        self._keepalive = []
 
     # -- lifecycle
     def close(self):
@@ -128,6 +131,14 @@ class TriplesEngine:
             k1 = min(self.o, k0 + step)
             part = flat[k0 * slab:k1 * slab]
             _lib.check(self.lib.pt_set_ppph_slabs(self._h, k0, k1, _ptr(part)))
+
+    def set_ppph_host(self, vabci):
+        """PPPHCoulombIntegrals kept in host memory; with ``slab_slots`` the engine uploads
+        slabs on demand, so the array is kept alive by this object."""
+        vabci = _f64(vabci)
+        self._shape(vabci, (self.v, self.v, self.v, self.o), "PPPHCoulombIntegrals")
+        self._keepalive.append(vabci)
+        _lib.check(self.lib.pt_set_ppph_host(self._h, _ptr(vabci)))
 
     def set_vertex(self, gamma):
         """CoulombVertex[NF,Np,Np] complex; PPPH is built on the device."""

@@ -145,6 +145,38 @@ def test_slabwise_upload_equals_bulk_upload():
     assert abs(a - golden(4, 33, "vertex", 17)[0]) <= ABS_TOL
 
 
+# ------------------------------------- hole-blocked PPPH residency (BASELINE configs[4] path)
+@pytest.mark.parametrize("slots", [3, 4, 6])
+@pytest.mark.parametrize("source", ["host", "vertex"])
+def test_slab_slots_equal_resident_run(slots, source):
+    """Only `slots` of the o PPPH slabs are resident; pt_run walks the triples by hole blocks and
+    re-fetches slabs (from the host tensor or rebuilt from the resident vertex).  Per-triple
+    energies must equal the all-resident run and the golden values."""
+    o, v = 7, 20
+    inp = S.make_inputs(o, v, seed=17, kind="vertex")
+    O = oracle()
+    e_ref, per_ref = O.triples_loop(*inp.args(), return_per_triple=True)
+    with TriplesEngine(o, v, slab_slots=slots) as eng:
+        eng.set_eigenenergies(inp.epsi, inp.epsa); eng.set_singles(inp.T1); eng.set_doubles(inp.T2)
+        eng.set_pphh(inp.Vpphh); eng.set_hhhp(inp.Vhhhp)
+        if source == "host":
+            eng.set_ppph_host(inp.Vppph)
+        else:
+            eng.set_vertex(inp.Gamma)
+        res = eng.run()
+        st = eng.stats()
+        assert st.slab_loads >= o                      # every slab was fetched at least once
+        assert abs(res.energy - e_ref) <= ABS_TOL
+        assert np.abs(res.per_triple - per_ref).max() <= ABS_TOL
+        # a partial range that starts in the middle of a hole block
+        b, e = eng.partition(3, 1)
+        part = eng.run(b, e)
+        assert np.abs(part.per_triple - per_ref[b:e]).max() <= ABS_TOL
+    with pytest.raises(_lib.PtError, match="slab_slots"):
+        with TriplesEngine(o, v, slab_slots=slots) as eng:
+            eng.set_ppph(inp.Vppph)
+
+
 def test_missing_input_is_an_error():
     inp = S.make_inputs(2, 5, seed=4, kind="random")
     with TriplesEngine(2, 5) as eng:
@@ -181,6 +213,54 @@ def test_yaml_plan_both_contracts():
     alg = AlgorithmFactory.create("PerturbativeTriples", dict(common), data)
     with pytest.raises(SisiException, match="Missing argument: PPPHCoulombIntegrals"):
         alg.run()
+
+
+def test_plan_file_with_tensor_readers(tmp_path, monkeypatch):
+    """`python -m sisi4s_b200 in.yaml`: inputs dumped in the reference's file formats (TENS binary,
+    text, cc4s yaml+elements, eigenenergy yaml), read back by the reference's reader steps and fed to
+    the (T) step -- the same plan a sisi4s user would write."""
+    from sisi4s_b200 import tensor_io as TIO
+    from sisi4s_b200.plan import run_plan_file
+    monkeypatch.chdir(tmp_path)
+    inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
+    e_ref = golden(5, 19, "vertex", 2026)[0]
+    TIO.write_binary("CcsdDoublesAmplitudes.bin", inp.T2)
+    TIO.write_binary("PPHHCoulombIntegrals.bin", inp.Vpphh)
+    TIO.write_binary("HHHPCoulombIntegrals.bin", inp.Vhhhp)
+    TIO.write_text("CcsdSinglesAmplitudes.dat", inp.T1, "CcsdSinglesAmplitudes")
+    TIO.write_cc4s("CoulombVertex.yaml", inp.Gamma, axis_types=["AuxiliaryField", "State", "State"])
+    en = ", ".join(repr(float(x)) for x in list(inp.epsi) + list(inp.epsa))
+    fermi = 0.5 * (float(inp.epsi.max()) + float(inp.epsa.min()))
+    open("EigenEnergies.yaml", "w").write(f"metaData:\n  fermiEnergy: {fermi!r}\n  energies: [{en}]\n")
+    open("in.yaml", "w").write(f"""
+- name: DefineHolesAndParticles
+  in: {{fileName: "EigenEnergies.yaml"}}
+  out: {{HoleEigenEnergies: $HoleEigenEnergies, ParticleEigenEnergies: $ParticleEigenEnergies}}
+- name: Read
+  in: {{fileName: "CoulombVertex.yaml"}}
+  out: {{destination: $CoulombVertex}}
+- {{name: TensorReader, in: {{mode: "binary"}}, out: {{Data: $CcsdDoublesAmplitudes}}}}
+- {{name: TensorReader, in: {{mode: "binary"}}, out: {{Data: $PPHHCoulombIntegrals}}}}
+- {{name: TensorReader, in: {{mode: "binary"}}, out: {{Data: $HHHPCoulombIntegrals}}}}
+- {{name: TensorReader, in: {{}}, out: {{Data: $CcsdSinglesAmplitudes}}}}
+- name: CcsdPerturbativeTriples
+  in:
+    CoulombVertex: $CoulombVertex
+    PPHHCoulombIntegrals: $PPHHCoulombIntegrals
+    HHHPCoulombIntegrals: $HHHPCoulombIntegrals
+    ParticleEigenEnergies: $ParticleEigenEnergies
+    HoleEigenEnergies: $HoleEigenEnergies
+    CcsdEnergy: {inp.ccsd_energy!r}
+    CcsdSinglesAmplitudes: $CcsdSinglesAmplitudes
+    CcsdDoublesAmplitudes: $CcsdDoublesAmplitudes
+  out:
+    CcsdPerturbativeTriplesEnergy: $CcsdPerturbativeTriplesEnergy
+- {{name: TensorWriter, in: {{Data: $CcsdPerturbativeTriplesEnergy}}}}
+""")
+    data = run_plan_file("in.yaml", log=lambda *_: None)
+    assert abs(data["CcsdPerturbativeTriplesEnergy"] - (inp.ccsd_energy + e_ref)) <= ABS_TOL
+    _, back = TIO.read_text("CcsdPerturbativeTriplesEnergy.dat")
+    assert abs(float(back.reshape(-1)[0]) - data["CcsdPerturbativeTriplesEnergy"]) <= 1e-14
 
 
 # ------------------------------------------------- full-size property (config 3 shape)

@@ -1,0 +1,112 @@
+"""Tensor file formats against the byte layouts the reference defines
+(BinaryTensorFormat.hpp:9-64, TensorIo.cxx, docs/manual.org:181-366) and plan parsing."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from sisi4s_b200 import tensor_io as TIO
+from sisi4s_b200.plan import parse_plan, run_plan_file
+from sisi4s_b200.triples import SisiException
+
+
+def test_binary_header_bytes_match_the_reference_struct(tmp_path):
+    a = np.arange(24, dtype=np.float64).reshape((2, 3, 4), order="F")
+    p = str(tmp_path / "A.bin")
+    TIO.write_binary(p, a)
+    raw = open(p, "rb").read()
+    # BinaryTensorHeaderBase: magic, version 0x09000, "IEEE", bytesPerNumber, numbersPerElement, order, flags, reserved
+    assert raw[:4] == b"TENS" and struct.unpack("<i", raw[4:8])[0] == 0x09000 and raw[8:12] == b"IEEE"
+    assert struct.unpack("<iiiii", raw[12:32]) == (8, 1, 3, 0, 0)
+    # BinaryTensorDimensionHeader: length, indexName 'a'+dim, flags, reserved (8 bytes each)
+    for dim, n in enumerate((2, 3, 4)):
+        off = 32 + 8 * dim
+        assert struct.unpack("<i", raw[off:off + 4])[0] == n and raw[off + 4:off + 5] == bytes([ord("a") + dim])
+    # dense data: ascending global index I = a + b*N0 + c*N0*N1 (docs/manual.org:320)
+    data = np.frombuffer(raw[32 + 24:], dtype="<f8")
+    assert np.array_equal(data, np.arange(24.0))
+    assert len(raw) == 32 + 24 + 24 * 8
+    b = TIO.read_binary(p)
+    assert b.shape == (2, 3, 4) and np.array_equal(a, b)
+    m = TIO.read_binary(p, mmap=True)
+    assert np.array_equal(np.asarray(m), a)
+
+
+def test_binary_complex_and_errors(tmp_path):
+    rng = np.random.default_rng(1)
+    g = rng.normal(size=(3, 4, 4)) + 1j * rng.normal(size=(3, 4, 4))
+    p = str(tmp_path / "G.bin")
+    TIO.write_binary(p, g)
+    raw = open(p, "rb").read()
+    assert struct.unpack("<ii", raw[12:20]) == (16, 2)     # sizeof(Complex<Real>), 2 numbers per element
+    assert np.array_equal(TIO.read_binary(p), g)
+    bad = str(tmp_path / "bad.bin")
+    open(bad, "wb").write(b"NOPE" + raw[4:])
+    with pytest.raises(TIO.TensorFormatError, match="Invalid file format"):
+        TIO.read_binary(bad)
+    newer = str(tmp_path / "newer.bin")
+    open(newer, "wb").write(raw[:4] + struct.pack("<i", 0x10000) + raw[8:])
+    with pytest.raises(TIO.TensorFormatError, match="Incompatible file format version"):
+        TIO.read_binary(newer)
+    with pytest.raises(FileNotFoundError, match="Failed to open file"):
+        TIO.read_binary(str(tmp_path / "missing.bin"))
+    open(bad, "wb").write(raw[:-8])
+    with pytest.raises(TIO.TensorFormatError, match="truncated"):
+        TIO.read_binary(bad)
+
+
+@pytest.mark.parametrize("row,col", [("", ""), ("ijk", ""), ("k", "ij"), ("ik", "j"), ("", "kji")])
+def test_text_round_trip_and_layout(tmp_path, row, col):
+    rng = np.random.default_rng(2)
+    a = rng.normal(size=(2, 3, 4))
+    p = str(tmp_path / "A.dat")
+    TIO.write_text(p, a, "A", row, col)
+    lines = open(p).read().splitlines()
+    assert lines[0] == "A 3 2 3 4"
+    name, b = TIO.read_text(p)
+    assert name == "A" and b.shape == a.shape and np.allclose(a, b, rtol=0, atol=1e-15 * np.abs(a).max() * 10)
+    if (row, col) == ("k", "ij"):
+        # one line per k, columns run over (i fastest, j)
+        assert len(lines) == 2 + 4
+        first = np.array(lines[2].split(), dtype=float)
+        assert np.allclose(first, a[:, :, 0].reshape(-1, order="F"), rtol=1e-15)
+
+
+def test_cc4s_yaml_elements_and_eigenenergies(tmp_path):
+    rng = np.random.default_rng(3)
+    g = rng.normal(size=(5, 6, 6)) + 1j * rng.normal(size=(5, 6, 6))
+    yp = str(tmp_path / "CoulombVertex.yaml")
+    TIO.write_cc4s(yp, g, binary=True, axis_types=["AuxiliaryField", "State", "State"])
+    assert os.path.exists(str(tmp_path / "CoulombVertex.elements"))
+    assert np.array_equal(TIO.read_cc4s(yp), g)
+    r = rng.normal(size=(4, 3))
+    rp = str(tmp_path / "R.yaml")
+    TIO.write_cc4s(rp, r, binary=False)
+    assert np.allclose(TIO.read_cc4s(rp), r, rtol=1e-15)
+    ep = str(tmp_path / "EigenEnergies.yaml")
+    open(ep, "w").write("metaData:\n  fermiEnergy: 0.0\n  energies: [-1.5, -0.7, -0.2, 0.3, 0.9, 1.4, 2.2]\n")
+    holes, parts = TIO.read_eigenenergies(ep)
+    assert np.array_equal(holes, [-1.5, -0.7, -0.2]) and np.array_equal(parts, [0.3, 0.9, 1.4, 2.2])
+
+
+def test_plan_parsing_and_file_algorithms(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    a = np.random.default_rng(4).normal(size=(3, 2))
+    TIO.write_binary("A.bin", a)
+    open("in.yaml", "w").write("""
+- name: Nop
+  tol: &tol 1e-8
+- name: TensorReader
+  in: {file: "A.bin", mode: "binary"}
+  out: {Data: $B}
+- name: TensorWriter
+  in: {Data: $B, rowIndexOrder: "j", columnIndexOrder: "i"}
+- {name: TensorReader, in: {file: "B.dat"}, out: {Data: $C}}
+""")
+    data = run_plan_file("in.yaml", log=lambda *_: None)
+    assert np.array_equal(data["B"], a) and np.allclose(data["C"], a, rtol=1e-15)
+    with pytest.raises(SisiException, match="not provided"):
+        open("bad.yaml", "w").write("- name: HartreeFockFromGaussian\n  in: {}\n")
+        run_plan_file("bad.yaml", log=lambda *_: None)
+    assert [n["name"] for n in parse_plan(open("in.yaml").read())] == ["TensorReader", "TensorWriter", "TensorReader"]
