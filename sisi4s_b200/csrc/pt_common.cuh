@@ -29,8 +29,8 @@
 namespace pt {
 
 constexpr int TILE = 16;
-constexpr int STAGE_DBL = 1152;            // doubles per pipeline stage (9216 B)
-constexpr int NSTAGE = 16;              // operand ring depth (X tiles live in TMEM, so the ring owns the smem)
+constexpr int STAGE_DBL = 2304;            // doubles per pipeline stage (18432 B: K = 8 of the particle contraction)
+constexpr int NSTAGE = 8;               // operand ring depth (X tiles live in TMEM, so the ring owns the smem)
 constexpr int XT_DBL = TILE * TILE * TILE; // one X tile
 constexpr int NCONSUMER_WARPS = 8;
 constexpr int NPRODUCER_WARPS = 4;          // stage j of the operand stream is issued by producer warp j % 4

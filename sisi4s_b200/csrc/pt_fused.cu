@@ -64,6 +64,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// one non-blocking probe; the result is consumed later (mbar_wait_tok), so that the SYNCS latency
+// hides behind the DMMA block issued in between
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_tok(uint32_t bar, uint32_t parity, uint32_t ok) {
+  if (!ok) mbar_wait(bar, parity);
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double x;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(x) : "r"(addr), "n"(OFF));
+  return x;
+}
 // 1-D bulk copy global -> shared, completion counted on an mbarrier (TMA engine)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -78,7 +100,7 @@ __device__ __forceinline__ void group_barrier(int grp) {
   asm volatile("bar.sync %0, %1;" ::"r"(2 + grp), "n"(NCONSUMER_WARPS * 16) : "memory");
 }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
@@ -112,6 +134,9 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 constexpr int TMEM_COLS = 512;
+// register split (setmaxnreg): 384 threads x 168 at launch = 8 x 32 x 224 + 4 x 32 x 56
+constexpr int CONSUMER_REGS = 224;
+constexpr int PRODUCER_REGS = 56;
 constexpr int TMEM_COLS_PER_TILE = 64;
 
 __device__ __forceinline__ int sel3(int a, int b, int c, int idx) {
@@ -175,26 +200,32 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
-// Stage j of a step: j < nk4 is particle chunk j (one 8 KB slab-tile chunk + the enabled
-// 512 B T2 panels), otherwise hole sub-stage lg = j - nk4 (per enabled half one 4 KB T2h
-// chunk + one 512 B HHHP panel chunk).
+// Stage j of a step (STAGE_DBL = 2304 doubles):
+//   j < nk8: particle chunks 2j, 2j+1 (K = 8): [V chunk 2j | V chunk 2j+1 | T0: 2 x 64 | T1: 2 x 64]
+//            = one 16 KB slab-tile copy + one 1 KB copy per enabled T2 panel (half of that for
+//            the odd tail chunk);
+//   else hole chunk lc = j - nk8 (K = 4, both b-halves g): [T2h half 0: 1024 | T2h half 1: 1024 |
+//            U0: 64 (+64 unused) | U1: 64] = one 8 KB + one 512 B copy per enabled half.
 __device__ __forceinline__ void issue_stage(const StepSrc& s, int j, int nk4, uint32_t stage, uint32_t full) {
   const uint32_t nen = (uint32_t)(s.en[0] + s.en[1]);
-  if (j < nk4) {
-    mbar_expect_tx(full, 8192u + 512u * nen);
-    bulk_g2s(stage, s.v + (size_t)j * 1024, 8192u, full);
-    if (s.en[0]) bulk_g2s(stage + 8192u, s.t[0] + (size_t)j * 64, 512u, full);
-    if (s.en[1]) bulk_g2s(stage + 8704u, s.t[1] + (size_t)j * 64, 512u, full);
+  const int nk8 = (nk4 + 1) >> 1;
+  if (j < nk8) {
+    const int c0 = 2 * j;
+    const uint32_t two = (c0 + 1 < nk4) ? 2u : 1u;
+    mbar_expect_tx(full, two * (8192u + 512u * nen));
+    bulk_g2s(stage, s.v + (size_t)c0 * 1024, two * 8192u, full);
+    if (s.en[0]) bulk_g2s(stage + 16384u, s.t[0] + (size_t)c0 * 64, two * 512u, full);
+    if (s.en[1]) bulk_g2s(stage + 17408u, s.t[1] + (size_t)c0 * 64, two * 512u, full);
   } else {
-    const int lg = j - nk4;
-    mbar_expect_tx(full, 4608u * nen);
+    const int lc = j - nk8;
+    mbar_expect_tx(full, 8704u * nen);
     if (s.en[0]) {
-      bulk_g2s(stage, s.hh[0] + (size_t)lg * 512, 4096u, full);
-      bulk_g2s(stage + 8192u, s.u[0] + (size_t)(lg >> 1) * 64, 512u, full);
+      bulk_g2s(stage, s.hh[0] + (size_t)lc * 1024, 8192u, full);
+      bulk_g2s(stage + 16384u, s.u[0] + (size_t)lc * 64, 512u, full);
     }
     if (s.en[1]) {
-      bulk_g2s(stage + 4096u, s.hh[1] + (size_t)lg * 512, 4096u, full);
-      bulk_g2s(stage + 8704u, s.u[1] + (size_t)(lg >> 1) * 64, 512u, full);
+      bulk_g2s(stage + 8192u, s.hh[1] + (size_t)lc * 1024, 8192u, full);
+      bulk_g2s(stage + 17408u, s.u[1] + (size_t)lc * 64, 512u, full);
     }
   }
 }
@@ -245,7 +276,7 @@ struct StageIter {
 // lane issues the copies.
 __device__ __forceinline__ void producer_loop(const FusedParams& p, const Pipe& pp0, uint32_t go_bar, int pw,
                                               long long first_item, int stride) {
-  const int nk4 = p.d.nk4, nst = nk4 + 2 * p.d.nl4;
+  const int nk4 = p.d.nk4, nst = ((nk4 + 1) >> 1) + p.d.nl4;
   StageIter ld;
   ld.item = first_item;
   ld.load_item(p);
@@ -277,18 +308,119 @@ __device__ __forceinline__ void producer_loop(const FusedParams& p, const Pipe& 
 // The two warps that share an SM sub-partition (w, w+4) therefore belong to different groups
 // and scatter into different X tiles, so no CTA barrier is needed between steps and one
 // group's scatter overlaps the other group's DMMA stream.
-__device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], const double* ring, Pipe& pp,
-                                             int nk4, int nl4, int en, int h, int wq, int lane) {
+//
+// Software pipeline (per warp): a "unit" is one K=4 chunk (16 DMMA, 10 LDS.64) or one hole
+// half-chunk (8 DMMA, 4-6 LDS.64); a stage holds two units.  The loads of unit n+1 (into the other
+// register buffer), the full-barrier wait of its stage, the release of a finished stage and the
+// probe of the next stage's barrier are all INTERLEAVED between the DMMAs of unit n, one
+// instruction per DMMA issue slot.  A warp therefore never leaves the DMMA stream: the two warps
+// that share an SM sub-partition's FP64 tensor pipe (issue interval 16 clk) cannot fall into a
+// common "fetch" phase during which the pipe would idle.  All shared addresses are one
+// per-thread base + slot * stage bytes + immediates.
+struct FragP { double b[4][2]; double a[2]; };
+struct FragH { double a[2][2]; };
+enum { NEXT_NONE = 0, NEXT_P0 = 1, NEXT_P1 = 2, NEXT_H0 = 3, NEXT_H1 = 4 };
+
+struct Consumer {
+  Pipe& pp;
+  uint32_t offB, offA, offH;  // per-thread fragment bases (shared byte addresses of stage 0)
+  uint32_t B, A, H;           // ... of the current stage
+  uint32_t tok;
+  bool lane0;
+  static constexpr uint32_t SB = STAGE_DBL * 8;
+
+  __device__ __forceinline__ void bind() {
+    const uint32_t sb = pp.slot * SB;
+    B = offB + sb; A = offA + sb; H = offH + sb;
+  }
+  __device__ __forceinline__ void probe() { tok = mbar_try(pp.full + 8 * pp.slot, pp.phase); }
+  __device__ __forceinline__ void await() {
+    mbar_wait_tok(pp.full + 8 * pp.slot, pp.phase, tok);
+    bind();
+  }
+  __device__ __forceinline__ void release() {  // this warp is done reading the current stage
+    __syncwarp();
+    if (lane0) mbar_arrive(pp.empty + 8 * pp.slot);
+    pp.advance();
+    probe();
+  }
+  // load n of the next unit (K = particle chunk half 0/1, hole half-chunk 0/1)
+  template <int NEXT, int N>
+  __device__ __forceinline__ void ld(FragP& fp, FragH& fh, double (&u)[2]) {
+    if constexpr (NEXT == NEXT_P0 || NEXT == NEXT_P1) {
+      constexpr int C = (NEXT == NEXT_P1) ? 1 : 0;
+      if constexpr (N < 8) fp.b[N >> 1][N & 1] = lds_f64<C * 8192 + (N >> 1) * 2048 + (N & 1) * 256>(B);
+      else if constexpr (N < 10) fp.a[N - 8] = lds_f64<C * 512 + (N - 8) * 256>(A);
+    } else if constexpr (NEXT == NEXT_H0 || NEXT == NEXT_H1) {
+      constexpr int G = (NEXT == NEXT_H1) ? 1 : 0;
+      if constexpr (N < 4) fh.a[N >> 1][N & 1] = lds_f64<G * 4096 + (N >> 1) * 2048 + (N & 1) * 256>(H);
+      else if constexpr (N < 6 && NEXT == NEXT_H0) u[N - 4] = lds_f64<(N - 4) * 256>(A);
+    }
+  }
+  template <int NEXT>
+  __host__ __device__ static constexpr int nloads() {
+    return (NEXT == NEXT_P0 || NEXT == NEXT_P1) ? 10 : (NEXT == NEXT_H0 ? 6 : (NEXT == NEXT_H1 ? 4 : 0));
+  }
+
+  // 16 DMMAs of particle chunk `cur`, with the next unit fetched in between
+  template <int NEXT>
+  __device__ __forceinline__ void block_p(double (&acc)[2][4][2][2], const FragP& cur, FragP& fp, FragH& fh,
+                                          double (&u)[2], bool last) {
+    constexpr int NL = nloads<NEXT>();
+    constexpr bool first = (NEXT == NEXT_P0 || NEXT == NEXT_H0);
+#define PT_DM(n) dmma(acc[(n) >> 3][((n) >> 1) & 3][(n) & 1][0], acc[(n) >> 3][((n) >> 1) & 3][(n) & 1][1], \
+                      cur.a[(n) >> 3], cur.b[((n) >> 1) & 3][(n) & 1])
+    PT_DM(0);
+    if constexpr (first) await();
+    ld<NEXT, 0>(fp, fh, u); PT_DM(1);
+    ld<NEXT, 1>(fp, fh, u); PT_DM(2);
+    ld<NEXT, 2>(fp, fh, u); PT_DM(3);
+    ld<NEXT, 3>(fp, fh, u); PT_DM(4);
+    ld<NEXT, 4>(fp, fh, u); PT_DM(5);
+    ld<NEXT, 5>(fp, fh, u); PT_DM(6);
+    ld<NEXT, 6>(fp, fh, u); PT_DM(7);
+    ld<NEXT, 7>(fp, fh, u); PT_DM(8);
+    ld<NEXT, 8>(fp, fh, u); PT_DM(9);
+    ld<NEXT, 9>(fp, fh, u); PT_DM(10);
+    if (NL > 0 && last) release();
+    PT_DM(11); PT_DM(12); PT_DM(13); PT_DM(14); PT_DM(15);
+#undef PT_DM
+  }
+  // 8 DMMAs of hole half-chunk g (columns bi = 2g + j)
+  template <int NEXT, int G>
+  __device__ __forceinline__ void block_h(double (&acc)[2][4][2][2], const FragH& cur, const double (&uc)[2],
+                                          FragP& fp, FragH& fh, double (&u)[2]) {
+    constexpr bool first = (NEXT == NEXT_H0);
+#define PT_DH(n) dmma(acc[(n) & 1][2 * G + ((n) >> 2)][((n) >> 1) & 1][0],                      \
+                      acc[(n) & 1][2 * G + ((n) >> 2)][((n) >> 1) & 1][1], cur.a[(n) >> 2][(n) & 1], \
+                      uc[((n) >> 1) & 1])
+    PT_DH(0);
+    if constexpr (first) await();
+    ld<NEXT, 0>(fp, fh, u); PT_DH(1);
+    ld<NEXT, 1>(fp, fh, u); PT_DH(2);
+    ld<NEXT, 2>(fp, fh, u); PT_DH(3);
+    ld<NEXT, 3>(fp, fh, u); PT_DH(4);
+    ld<NEXT, 4>(fp, fh, u); PT_DH(5);
+    ld<NEXT, 5>(fp, fh, u);
+    if constexpr (NEXT == NEXT_H1) release();
+    PT_DH(6); PT_DH(7);
+#undef PT_DH
+  }
+};
+
+__device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], Pipe& pp, int nk4, int nl4, int en,
+                                             int h, int wq, int lane) {
 #pragma unroll
   for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
     for (int bi = 0; bi < 4; ++bi)
 #pragma unroll
       for (int co = 0; co < 2; ++co) acc[mf][bi][co][0] = acc[mf][bi][co][1] = 0.0;
+  const int nk8 = (nk4 + 1) >> 1;
 
   if (!en) {
     // disabled half: keep the stage accounting going
-    const int n = nk4 + 2 * nl4;
+    const int n = nk8 + nl4;
     for (int s = 0; s < n; ++s) {
       mbar_wait(pp.full + 8 * pp.slot, pp.phase);
       __syncwarp();
@@ -298,79 +430,41 @@ __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], const do
     return;
   }
 
-  // Operand fragments are double-buffered in registers: the fragments of stage n+1 are
-  // fetched (and its ring slot released) before the DMMAs of stage n issue, which makes the
-  // register file a fourth pipeline stage.
+  Consumer c{pp};
+  c.offB = pp.ring + (uint32_t)(wq * 64 + lane) * 8u;            // + chunk*8192 + bi*2048 + co*256
+  c.offA = pp.ring + (uint32_t)(2048 + h * 128 + lane) * 8u;     // + chunk*512 + mf*256  (U: + co*256)
+  c.offH = pp.ring + (uint32_t)(h * 1024 + wq * 64 + lane) * 8u; // + g*4096 + j*2048 + mf*256
+  c.lane0 = lane == 0;
+
+  FragP fA, fB;
+  FragH hA, hB;
+  double uf[2], un[2];
+  // prologue: chunk 0 of the first stage
+  c.probe();
+  c.await();
+  c.ld<NEXT_P0, 0>(fA, hA, uf); c.ld<NEXT_P0, 1>(fA, hA, uf); c.ld<NEXT_P0, 2>(fA, hA, uf);
+  c.ld<NEXT_P0, 3>(fA, hA, uf); c.ld<NEXT_P0, 4>(fA, hA, uf); c.ld<NEXT_P0, 5>(fA, hA, uf);
+  c.ld<NEXT_P0, 6>(fA, hA, uf); c.ld<NEXT_P0, 7>(fA, hA, uf); c.ld<NEXT_P0, 8>(fA, hA, uf);
+  c.ld<NEXT_P0, 9>(fA, hA, uf);
+  if (nk4 == 1) c.release();
   // ---- particle contraction: W[a,b,c] += sum_d T2[a,d,x,y] V[b,c,d,z]
-  auto ld_p = [&](double (&bf)[4][2], double (&af)[2]) {
-    const double* st = ring + pp.slot * STAGE_DBL;
-    mbar_wait(pp.full + 8 * pp.slot, pp.phase);
-#pragma unroll
-    for (int bi = 0; bi < 4; ++bi)
-#pragma unroll
-      for (int co = 0; co < 2; ++co) bf[bi][co] = st[((wq + 4 * bi) * 2 + co) * 32 + lane];
-#pragma unroll
-    for (int mf = 0; mf < 2; ++mf) af[mf] = st[1024 + h * 64 + mf * 32 + lane];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
-    pp.advance();
-  };
-  auto mma_p = [&](const double (&bf)[4][2], const double (&af)[2]) {
-#pragma unroll
-    for (int mf = 0; mf < 2; ++mf)
-#pragma unroll
-      for (int bi = 0; bi < 4; ++bi)
-#pragma unroll
-        for (int co = 0; co < 2; ++co) dmma(acc[mf][bi][co][0], acc[mf][bi][co][1], af[mf], bf[bi][co]);
-  };
-  // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); sub-stage g covers
-  //      b = 8g .. 8g+7, of which this warp owns b = 8g + wq + 4j  (bi = 2g + j)
-  auto ld_h = [&](double (&af)[2][2], double (&uf)[2]) {
-    const double* st = ring + pp.slot * STAGE_DBL;
-    mbar_wait(pp.full + 8 * pp.slot, pp.phase);
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int mf = 0; mf < 2; ++mf) af[j][mf] = st[h * 512 + (wq + 4 * j) * 64 + mf * 32 + lane];
-#pragma unroll
-    for (int co = 0; co < 2; ++co) uf[co] = st[1024 + h * 64 + co * 32 + lane];
-    __syncwarp();
-    if (lane == 0) mbar_arrive(pp.empty + 8 * pp.slot);
-    pp.advance();
-  };
-  {
-    double bfA[4][2], afA[2], bfB[4][2], afB[2];
-    double hfA[2][2], ufA[2], hfB[2][2], ufB[2];
-    ld_p(bfA, afA);
-    int dc = 0;
-    for (; dc + 1 < nk4; dc += 2) {
-      ld_p(bfB, afB);
-      mma_p(bfA, afA);
-      if (dc + 2 < nk4) ld_p(bfA, afA); else ld_h(hfA, ufA);
-      mma_p(bfB, afB);
-    }
-    if (nk4 & 1) {
-      ld_h(hfA, ufA);
-      mma_p(bfA, afA);
-    }
-    // hfA/ufA hold hole sub-stage (lc = 0, g = 0)
-    for (int lc = 0; lc < nl4; ++lc) {
-      ld_h(hfB, ufB);  // (lc, g = 1)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int mf = 0; mf < 2; ++mf)
-#pragma unroll
-          for (int co = 0; co < 2; ++co) dmma(acc[mf][j][co][0], acc[mf][j][co][1], hfA[j][mf], ufA[co]);
-      if (lc + 1 < nl4) ld_h(hfA, ufA);  // (lc + 1, g = 0)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int mf = 0; mf < 2; ++mf)
-#pragma unroll
-          for (int co = 0; co < 2; ++co) dmma(acc[mf][2 + j][co][0], acc[mf][2 + j][co][1], hfB[j][mf], ufB[co]);
-    }
+  int dc = 0;
+  for (; dc + 1 < nk4; dc += 2) {
+    c.block_p<NEXT_P1>(acc, fA, fB, hB, un, true);                      // chunk dc; fetch dc+1, stage done
+    if (dc + 2 < nk4) c.block_p<NEXT_P0>(acc, fB, fA, hA, uf, dc + 3 >= nk4);  // chunk dc+1; fetch dc+2
+    else c.block_p<NEXT_H0>(acc, fB, fA, hA, uf, false);                // chunk dc+1; fetch hole (0, g=0)
   }
+  if (nk4 & 1) c.block_p<NEXT_H0>(acc, fA, fB, hA, uf, false);          // tail chunk; fetch hole (0, g=0)
+  // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); half-chunk g covers
+  //      b = 8g .. 8g+7, of which this warp owns b = 8g + wq + 4j  (bi = 2g + j)
+  for (int lc = 0; lc + 1 < nl4; ++lc) {
+    c.block_h<NEXT_H1, 0>(acc, hA, uf, fA, hB, un);
+    c.block_h<NEXT_H0, 1>(acc, hB, uf, fA, hA, un);
+    uf[0] = un[0];
+    uf[1] = un[1];
+  }
+  c.block_h<NEXT_H1, 0>(acc, hA, uf, fA, hB, un);
+  c.block_h<NEXT_NONE, 1>(acc, hB, uf, fA, hA, un);
 }
 
 __host__ __device__ constexpr int bitswap13(int v) { return (v & 5) | ((v & 2) << 2) | ((v & 8) >> 2); }
@@ -553,12 +647,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   const uint32_t go_bar = smem_u32(bars + 2 * NSTAGE);
 
   if (warp >= NCONSUMER_WARPS) {
-    // ===== producer warps =====
+    // ===== producer warps (one warpgroup): hand registers to the consumers =====
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS));
     producer_loop(p, pp, go_bar, warp - NCONSUMER_WARPS, blockIdx.x, gridDim.x);
     return;
   }
 
-  // ===== consumer warps =====
+  // ===== consumer warps (two warpgroups) =====
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CONSUMER_REGS));
   const int grp = warp >> 2, wq = warp & 3;
   const uint32_t tmem_lane_base = tmem_base + ((uint32_t)(32 * wq) << 16);
   double* my_stg = stg + grp * XT_DBL;
@@ -577,7 +673,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   // without CTA barriers between steps, accesses of one X element / staging word by different
   // warps are ordered through the stage ring (a warp can run at most NSTAGE stages ahead of
   // the slowest one); that needs steps of more than NSTAGE stages
-  const bool step_sync_always = (nk4 + 2 * nl4) < 2 * NSTAGE;
+  const bool step_sync_always = (((nk4 + 1) >> 1) + nl4) < 2 * NSTAGE;
   for (long long item = blockIdx.x; item < p.nitems; item += gridDim.x) {
     int t, orb;
     decode_item(p, item, t, orb);
@@ -590,7 +686,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       const PtStep& st = tab.steps[s];
       const PtHalf& hf = st.h[grp];
       double acc[2][4][2][2];
-      consume_step(acc, ring, pp, nk4, nl4, (p.debug & 1) ? 0 : hf.en, grp, wq, lane);
+      consume_step(acc, pp, nk4, nl4, (p.debug & 1) ? 0 : hf.en, grp, wq, lane);
       // the halves of a step target different X tiles except in orbits with coinciding
       // ranges; only then (or for very short steps) are the two scatters separated by barriers
       const bool sync = step_sync_always || (st.h[0].en && st.h[1].en && st.h[0].tau == st.h[1].tau);
@@ -737,7 +833,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
   if (warp > NCONSUMER_WARPS) return;
   if (warp == NCONSUMER_WARPS) {
     const bool leader = elect_one();
-    const int nst = p.d.nk4 + 2 * p.d.nl4;
+    const int nst = ((p.d.nk4 + 1) >> 1) + p.d.nl4;
     for (int j = 0; j < nst; ++j) {
       mbar_wait(pp.empty + 8 * pp.slot, pp.phase ^ 1);
       if (leader) issue_stage(src, j, p.d.nk4, pp.ring + pp.slot * (STAGE_DBL * 8), pp.full + 8 * pp.slot);
@@ -747,7 +843,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
   }
   const int grp = warp >> 2, wq = warp & 3;
   double acc[2][4][2][2];
-  consume_step(acc, ring, pp, p.d.nk4, p.d.nl4, grp == 0, grp, wq, lane);
+  consume_step(acc, pp, p.d.nk4, p.d.nl4, grp == 0, grp, wq, lane);
   if (grp != 0) return;
 #pragma unroll
   for (int mf = 0; mf < 2; ++mf)
