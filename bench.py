@@ -29,9 +29,13 @@ import sys
 import threading
 import time
 
-# N ranks share the host cores during the (untimed) input generation
-if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 8) // int(os.environ["WORLD_SIZE"]))))
+# Host threads.  torchrun exports OMP_NUM_THREADS=1 unless it is already set; the (untimed) input
+# generation then shares the host cores between the N ranks, and the reference arm -- which runs on
+# rank 0 alone -- takes all of them.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    _cores = os.cpu_count() or 8
+    _ref = "--impl" in sys.argv and "reference" in sys.argv
+    os.environ["OMP_NUM_THREADS"] = str(_cores if _ref else max(1, _cores // int(os.environ["WORLD_SIZE"])))
 
 import numpy as np
 
@@ -308,7 +312,7 @@ def main():
                "energy": e_e2e + inp.ccsd_energy, "triples_energy": e_e2e}
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # reported at N=1 only
         pool = [int(t) for t in np.linspace(40, weights.size - 40, 24).astype(int)]
         cpu = cpu_baseline_sample(inp, pool, weights)
 
@@ -317,10 +321,11 @@ def main():
         prof = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
         if os.path.exists(prof):
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                # measured on one N=1 step (profiles/r01d_step_traffic.csv); a rank's launch covers 1/world of it
+                traffic = json.load(open(prof)).get("dram_bytes_per_launch") / world
             except Exception:
                 traffic = None
-        achieved = fl_all / k_max * 1e-12
+        achieved = fl_all / world / k_max * 1e-12   # per GPU: the roofline is the kernel's, not the job's
         line = {
             "metric": "(T) FP64 TFLOP/s at o=40,v=300", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3,
@@ -338,7 +343,8 @@ def main():
                          "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (burst; "
                                         f"sustained median {peak_sust:.2f}); MEASURED_PEAKS.json has no FP64 entry",
                          "frac_of_nominal_37": achieved / 37.0,
-                         "kernel": "pt_fused_kernel", "algorithmic_flop": fl_all},
+                         "kernel": "pt_fused_kernel", "algorithmic_flop": fl_all / world,
+                         "per": "GPU (slowest rank's kernel time)"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

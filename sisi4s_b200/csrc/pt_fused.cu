@@ -762,21 +762,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       const int x0 = tid & 15, x1 = tid >> 4;
       const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
       const double d01 = e3 - tv[48 + x0] - tv[64 + x1];
-      const double t0 = tv[x0], t1v = tv[16 + x1];
-#pragma unroll 4
+      const double t0 = 0.5 * tv[x0], t1v = 0.5 * tv[16 + x1];
+      const double q2c = 0.5 * Qs[512 + x0 + 16 * x1];
+      // xt_index(a,b,c) = (a ^ b ^ s(c)) + 16 b + 256 c with s = bitswap13 (XOR-linear): the six
+      // permuted reads share three low nibbles, each a per-thread constant XOR a function of x2
+      const int l01 = x0 ^ x1, l25 = x1 ^ bitswap13(x0), l34 = x0 ^ bitswap13(x1);
+      const double* P0 = Xt + 16 * x1;
+      const double* P1 = X1 + 16 * x0;
+      const double* P2 = X2 + 256 * x0;
+      const double* P3 = X3 + 256 * x1;
+      const double* P4 = X4 + 16 * x0 + 256 * x1;
+      const double* P5 = X5 + 16 * x1 + 256 * x0;
+      const double* Q0 = Qs + x1;
+      const double* Q1 = Qs + 256 + x0;
+      const int nv2 = min(16, v - gc0);   // valid x2 of this tile (>= 1)
+#pragma unroll
       for (int x2 = 0; x2 < 16; ++x2) {
         // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}; nbr[tl][0] == tl (identity)
-        const double xd = Xt[xt_index(x0, x1, x2)];
+        const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
+        const double xd = P0[a01 + 256 * x2];
         double zn = c0 * xd;
-        zn += c1 * X1[xt_index(x1, x0, x2)];
-        zn += c2 * X2[xt_index(x1, x2, x0)];
-        zn += c3 * X3[xt_index(x0, x2, x1)];
-        zn += c4 * X4[xt_index(x2, x0, x1)];
-        zn += c5 * X5[xt_index(x2, x1, x0)];
-        const double sd = 0.5 * (t0 * Qs[x1 + 16 * x2] + t1v * Qs[256 + x0 + 16 * x2] +
-                                 tv[32 + x2] * Qs[512 + x0 + 16 * x1]);
+        zn += c1 * P1[a01 + 256 * x2];
+        zn += c2 * P2[a25 + 16 * x2];
+        zn += c3 * P3[a34 + 16 * x2];
+        zn += c4 * P4[a34];
+        zn += c5 * P5[a25];
+        const double sd = t0 * Q0[16 * x2] + t1v * Q1[16 * x2] + tv[32 + x2] * q2c;
         const double dd = d01 - tv[80 + x2];
-        if (valid01 && (gc0 + x2 < v)) e_acc += (xd + sd) * zn / dd;
+        if (valid01 && x2 < nv2) e_acc += (xd + sd) * zn / dd;
       }
       consumer_barrier();
     }

@@ -112,14 +112,28 @@ def make_vertex(o: int, v: int, seed: int = 2026, nf: int | None = None,
     return np.asfortranarray(R + 1j * I)
 
 
-def integrals_from_vertex(Gamma: np.ndarray, o: int, v: int):
+def ppph_slab_from_vertex(Gamma: np.ndarray, o: int, v: int, i: int) -> np.ndarray:
+    """One hole slab Vabci[:,:,:,i] = G[G,a,c] G[G,b,i] (Re.Re + Im.Im), column-major [v,v,v]
+    (CoulombIntegralsFromVertex.cxx:430-431) -- for shapes whose whole v^3 o tensor is not wanted
+    on the host."""
+    nf, np_, _ = Gamma.shape
+    a0 = np_ - v
+    X = None
+    for G in (Gamma.real, Gamma.imag):
+        Gca = np.ascontiguousarray(G[:, a0:, a0:].transpose(0, 2, 1)).reshape(nf, v * v)  # [F,(c,a)]
+        Gb = np.ascontiguousarray(G[:, a0:, i].T)                                          # [b,F]
+        X = Gb @ Gca if X is None else X + Gb @ Gca                                        # [b,(c,a)]
+    return np.asfortranarray(X.reshape(v, v, v).transpose(2, 0, 1))
+
+
+def integrals_from_vertex(Gamma: np.ndarray, o: int, v: int, with_ppph: bool = True):
     """CoulombIntegralsFromVertex.cxx:399-433 (real integrals), as GEMMs."""
     nf, np_, _ = Gamma.shape
     a0 = np_ - v
     Gr, Gi = np.ascontiguousarray(Gamma.real), np.ascontiguousarray(Gamma.imag)
     Vpphh = np.zeros((v, v, o, o))
     Vhhhp = np.zeros((o, o, o, v))
-    Vppph = np.empty((v, v, v, o), order="F")
+    Vppph = np.empty((v, v, v, o), order="F") if with_ppph else None
     parts = []
     for G in (Gr, Gi):
         Gij = G[:, :o, :o].reshape(nf, o * o)      # [F,(i,k)]
@@ -128,12 +142,14 @@ def integrals_from_vertex(Gamma: np.ndarray, o: int, v: int):
         Vpphh += (Gai.T @ Gai).reshape(v, o, v, o).transpose(0, 2, 1, 3)
         # Vijka[i,j,k,a] = G[G,i,k] G[G,a,j]
         Vhhhp += (Gij.T @ Gai).reshape(o, o, v, o).transpose(0, 3, 1, 2)
+        if not with_ppph:
+            continue
         # operands of Vabci, laid out so each hole slab is one GEMM
         Gca = np.ascontiguousarray(G[:, a0:, a0:].transpose(0, 2, 1)).reshape(nf, v * v)  # [F,(c,a)]
         Gib = np.ascontiguousarray(G[:, a0:, :o].transpose(2, 1, 0))                       # [i,b,F]
         parts.append((Gca, Gib))
     # Vabci[a,b,c,i] = G[G,a,c] G[G,b,i], one column-major v^3 slab per hole i
-    for i in range(o):
+    for i in range(o if with_ppph else 0):
         X = parts[0][1][i] @ parts[0][0]
         X += parts[1][1][i] @ parts[1][0]          # [b,(c,a)]
         Vppph[:, :, :, i] = X.reshape(v, v, v).transpose(2, 0, 1)
@@ -141,11 +157,13 @@ def integrals_from_vertex(Gamma: np.ndarray, o: int, v: int):
 
 
 def make_inputs(o: int, v: int, seed: int = 2026, kind: str = "vertex",
-                nf: int | None = None, kappa: float | None = None) -> TriplesInputs:
+                nf: int | None = None, kappa: float | None = None, with_ppph: bool = True) -> TriplesInputs:
+    """``with_ppph=False`` (kind "vertex" only) leaves ``Vppph`` None: large shapes hand the vertex
+    to the engine, which builds the PPPH slabs on the device."""
     epsi, epsa = eigenenergies(o, v)
     if kind == "vertex":
         Gamma = make_vertex(o, v, seed, nf, kappa)
-        Vpphh, Vhhhp, Vppph = integrals_from_vertex(Gamma, o, v)
+        Vpphh, Vhhhp, Vppph = integrals_from_vertex(Gamma, o, v, with_ppph)
         D2 = (epsi[None, None, :, None] + epsi[None, None, None, :]
               - epsa[:, None, None, None] - epsa[None, :, None, None])
         T2 = np.asfortranarray(Vpphh / D2)
