@@ -45,6 +45,14 @@ sys.path.insert(0, ROOT)
 O_, V_ = 40, 300
 NBATCH = 8
 NF_SYNTH = 24  # auxiliary index of the synthetic vertex (setup cost only; not on the timed path)
+# --workload: (o, v, steps per complete E(T), PPPH on the host?, BASELINE.json config)
+WORKLOADS = {
+    "o40v300": (40, 300, 8, True, "configs[2]"),     # the configuration the metric is quoted on (default)
+    "o20v100": (20, 100, 1, True, "configs[1]"),
+    "o64v512": (64, 512, 64, False, "configs[3]"),   # 96.6 GB per GPU; PPPH built on the device from the vertex
+}
+HOST_PPPH = True
+CONFIG_NAME = "configs[2]"
 
 
 def flops_of(o, v, weight):
@@ -159,6 +167,10 @@ def run_reference_arm(args, rank, world):
     (oracle/pt_oracle.c, OpenMP over all host cores) on a bounded sample per step."""
     if rank != 0:
         return
+    if not HOST_PPPH:
+        print(json.dumps({"impl": "reference", "unavailable": f"workload {args.workload}: the CPU arm needs the "
+                          "v^3 o PPPH tensor on the host; timed at o40v300 / o20v100 only"}), flush=True)
+        return
     from oracle import c_oracle as CO
     from sisi4s_b200 import synthetic as S
     inp = S.make_inputs(O_, V_, seed=2026, kind="vertex", nf=NF_SYNTH)
@@ -179,10 +191,10 @@ def run_reference_arm(args, rank, world):
     el = time.time() - t0
     val = fl / el * 1e-12
     line = {
-        "impl": "reference", "metric": "(T) FP64 TFLOP/s at o=40,v=300", "value": val, "unit": "TFLOP/s",
+        "impl": "reference", "metric": f"(T) FP64 TFLOP/s at o={O_},v={V_}", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic UEG-style (T), o={O_} v={V_} (BASELINE configs[2])", "o": O_, "v": V_,
+        "config": {"workload": f"synthetic UEG-style (T), o={O_} v={V_} (BASELINE {CONFIG_NAME})", "o": O_, "v": V_,
                    "step": f"bounded sample: {per_step} sorted triples of the step's eighth of the triple list"},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": CO.max_threads(), "kind": "port",
                          "sample": f"{per_step} sorted triples per step, {args.steps} steps; C restatement of "
@@ -196,12 +208,17 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=NBATCH)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="o40v300", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
+    global O_, V_, NBATCH, HOST_PPPH, CONFIG_NAME
+    O_, V_, NBATCH, HOST_PPPH, CONFIG_NAME = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = min(NBATCH, 8)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -236,18 +253,19 @@ def main():
 
     # ---- setup (untimed): inputs, FP64 ceiling, upload + pack
     t_setup = time.time()
-    inp = S.make_inputs(O_, V_, seed=2026, kind="vertex", nf=NF_SYNTH)
+    inp = S.make_inputs(O_, V_, seed=2026, kind="vertex", nf=NF_SYNTH, with_ppph=HOST_PPPH)
     # the large tensors live in page-locked host memory from here on (one copy per rank: the
     # pageable originals are dropped, so that 8 ranks fit the host's memory)
     keep = []
-    for field in ("T2", "Vpphh", "Vppph", "Vhhhp"):
+    for field in ("T2", "Vpphh", "Vppph", "Vhhhp") if HOST_PPPH else ("T2", "Vpphh", "Vhhhp"):
         view, owner = pinned_like(getattr(inp, field))
         setattr(inp, field, view)
         keep.append(owner)
     weights = triple_weights(O_)
     peak_burst, peak_sust = measure_fp64_peak(dev)
     eng = TriplesEngine(O_, V_, device=local)
-    eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph)
+    eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph,
+                   vertex=None if HOST_PPPH else inp.Gamma)
     t_setup = time.time() - t_setup
 
     def step_range(s):
@@ -281,9 +299,13 @@ def main():
 
     # ---- end-to-end leg: plugin API, host (pinned) buffers -> energy
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and NBATCH <= 8:   # larger workloads: one complete E(T) takes > 20 min on one GPU
         big = dict(CcsdDoublesAmplitudes=inp.T2, PPHHCoulombIntegrals=inp.Vpphh,
-                   PPPHCoulombIntegrals=inp.Vppph, HHHPCoulombIntegrals=inp.Vhhhp)   # pinned (see setup)
+                   HHHPCoulombIntegrals=inp.Vhhhp)   # pinned (see setup)
+        if HOST_PPPH:
+            big["PPPHCoulombIntegrals"] = inp.Vppph
+        else:
+            big["CoulombVertex"] = inp.Gamma         # PPPH is built on the device
         data = dict(HoleEigenEnergies=inp.epsi, ParticleEigenEnergies=inp.epsa, CcsdEnergy=inp.ccsd_energy,
                     CcsdSinglesAmplitudes=inp.T1, **big)
         argsmap = {k: "$" + k for k in data}
@@ -312,7 +334,7 @@ def main():
                "energy": e_e2e + inp.ccsd_energy, "triples_energy": e_e2e}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:   # reported at N=1 only
+    if rank == 0 and world == 1 and HOST_PPPH and not args.no_cpu:   # reported at N=1 only
         pool = [int(t) for t in np.linspace(40, weights.size - 40, 24).astype(int)]
         cpu = cpu_baseline_sample(inp, pool, weights)
 
@@ -327,15 +349,15 @@ def main():
                 traffic = None
         achieved = fl_all / world / k_max * 1e-12   # per GPU: the roofline is the kernel's, not the job's
         line = {
-            "metric": "(T) FP64 TFLOP/s at o=40,v=300", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "metric": f"(T) FP64 TFLOP/s at o={O_},v={V_}", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"synthetic UEG-style (T), o={O_} v={V_} (BASELINE configs[2])", "o": O_, "v": V_,
+            "config": {"workload": f"synthetic UEG-style (T), o={O_} v={V_} (BASELINE {CONFIG_NAME})", "o": O_, "v": V_,
                        "step": f"1/{NBATCH} of the sorted-triple list (weight-balanced contiguous chunk) per step, "
                                f"split over {world} rank(s); {NBATCH} steps = one complete E(T)",
                        "parallelism": f"triples sharded over {world} GPU(s), inputs replicated",
-                       "l2": "inputs (11 GB/GPU) are much larger than the 126 MB L2; no flush needed",
+                       "l2": "inputs (>= 0.2 GB/GPU packed; 11 GB at o=40,v=300) exceed the 126 MB L2; no flush needed",
                        "triples_energy_of_timed_steps": e_all, "wall_s_timed": wall,
                        "wall_s_full_problem_est": t_max / args.steps * NBATCH, "setup_s": t_setup},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",

@@ -79,6 +79,11 @@ void CcsdPerturbativeTriplesGpu::run() {
 
   pt_handle_t h(nullptr);
   PT_CHECK(pt_create(&h, No, Nv, device));
+  // optional: hole-blocked residency of V_abci for shapes whose v^3 o tensor exceeds the GPU's
+  // memory (slabSlots >= 3 slabs resident; the rest is rebuilt from the vertex / re-uploaded)
+  const int64_t slabSlots(getIntegerArgument("slabSlots", 0));
+  if (slabSlots > 0) PT_CHECK(pt_set_option(h, "slab_slots", slabSlots));
+  std::vector<double> hostPpph; // must outlive pt_run in the blocked PPPH contract
 
   {
     std::vector<double> ei(gather(epsi)), ea(gather(epsa));
@@ -113,6 +118,10 @@ void CcsdPerturbativeTriplesGpu::run() {
     // so that no rank ever holds more than v^3 doubles of V_abci on the host
     Tensor<double> *Vabci(getTensorArgument("PPPHCoulombIntegrals"));
     expectShape(Vabci, {Nv, Nv, Nv, No}, "PPPHCoulombIntegrals");
+    if (slabSlots > 0 && slabSlots < No) {
+      hostPpph = gather(Vabci);
+      PT_CHECK(pt_set_ppph_host(h, hostPpph.data()));
+    } else
     for (int k(0); k < No; ++k) {
       int start[] = {0, 0, 0, k}, end[] = {Nv, Nv, Nv, k + 1};
       Tensor<double> slab(Vabci->slice(start, end));

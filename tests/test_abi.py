@@ -88,3 +88,22 @@ def test_plugin_mirror_argument_errors():
         alg.setRealArgument("CcsdPerturbativeTriplesEnergy", 1.0)
     assert AlgorithmFactory.create("NoSuchAlgorithm", {}, data) is None
     assert AlgorithmFactory.create("PerturbativeTriples", {}, data).getName() == "PerturbativeTriples"
+
+
+def test_plugin_class_compiles_against_reference_headers():
+    """The C++ drop-in class (CcsdPerturbativeTriplesGpu.cxx) is syntax-checked against the
+    reference's OWN headers where they lie (src/algorithms/Algorithm.hpp, Data.hpp, DryTensor.hpp,
+    util/*.hpp); only the absent third-party headers <ctf.hpp> and <mpi.h> are stand-ins
+    (tests/stubs/).  Needs /root/reference, which exists in the build container only."""
+    import shutil
+    import subprocess
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref) or shutil.which("g++") is None:
+        pytest.skip("reference sources / g++ not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(root, "tests", "stubs"), "-I", ref,
+           "-I", os.path.join(root, "include"), "-I", cuda_inc, "-I", os.path.join(root, "sisi4s_b200", "csrc"),
+           os.path.join(root, "sisi4s_b200", "csrc", "CcsdPerturbativeTriplesGpu.cxx")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
