@@ -1,0 +1,28 @@
+"""A/B timing of library builds and debug switches on one (40,300) bench step.
+usage: python scripts/ab_timing.py lib1.so[:debug,debug,...] lib2.so[:...]   (run each in a subprocess)"""
+import json, os, subprocess, sys
+HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import json, os, sys
+sys.path.insert(0, %r)
+from sisi4s_b200 import synthetic as S
+from sisi4s_b200.triples import TriplesEngine
+dbg = [int(x) for x in sys.argv[1].split(",")]
+inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
+with TriplesEngine(40, 300) as eng:
+    eng.set_inputs(*inp.args())
+    b, e = eng.partition(8, 3)
+    eng.run(b, b + 200)
+    for d in dbg:
+        eng.set_option("debug", d)
+        r = eng.run(b, e)
+        print(json.dumps({"lib": os.path.basename(os.environ.get("SISI4S_PT_LIB", "default")), "debug": d,
+                          "s_kernel": r.seconds_kernel, "tflops_equiv": r.flops / r.seconds_kernel * 1e-12,
+                          "E": r.energy}), flush=True)
+''' % HERE
+for spec in sys.argv[1:]:
+    lib, _, dbg = spec.partition(":")
+    env = dict(os.environ)
+    if lib != "default":
+        env["SISI4S_PT_LIB"] = os.path.join(HERE, "sisi4s_b200", lib)
+    subprocess.run([sys.executable, "-c", CHILD, dbg or "0"], env=env, check=False)

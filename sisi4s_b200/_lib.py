@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsisi4s_pt.so")
+LIB_PATH = os.environ.get("SISI4S_PT_LIB") or os.path.join(_HERE, "libsisi4s_pt.so")   # override: A/B builds
 
 PT_ENGINE_FUSED = 0
 PT_ENGINE_NAIVE = 1

@@ -48,7 +48,7 @@ struct PtHandle_ {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // raw device tensors
-  double *epsi = nullptr, *epsa = nullptr, *t1 = nullptr, *pphh = nullptr;
+  double *epsi = nullptr, *epsa = nullptr, *t1 = nullptr, *pphh = nullptr, *qsum = nullptr;
   double *t2_raw = nullptr, *hhhp_raw = nullptr, *ppph_raw = nullptr;  // keep_raw only
   // packed
   double *Tt = nullptr, *T2h = nullptr, *Vt = nullptr, *Ut = nullptr;
@@ -198,7 +198,7 @@ int pt_destroy(pt_handle_t h) {
   if (!h) return PT_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  double* ptrs[] = {h->epsi, h->epsa, h->t1, h->pphh, h->t2_raw, h->hhhp_raw, h->ppph_raw,
+  double* ptrs[] = {h->epsi, h->epsa, h->t1, h->pphh, h->qsum, h->t2_raw, h->hhhp_raw, h->ppph_raw,
                     h->Tt, h->T2h, h->Vt, h->Ut, h->slab_stage, h->g_re, h->g_im};
   for (double* p : ptrs)
     if (p) cudaFree(p);
@@ -268,6 +268,9 @@ int pt_set_pphh(pt_handle_t h, const double* vabij) {
   const size_t n = (size_t)h->d.v * h->d.v * h->d.o * h->d.o;
   if (!h->pphh) CU(h->alloc(&h->pphh, n));
   if (int rc = upload(h, h->pphh, vabij, n)) return rc;
+  if (!h->qsum) CU(h->alloc(&h->qsum, n));
+  CU(launch_pphh_symsum(h->pphh, h->qsum, h->d, h->stream));
+  h->stats.kernel_launches += 1;
   h->stats.seconds_upload += tm.stop();
   h->have_pphh = true;
   return PT_OK;
@@ -458,7 +461,7 @@ static FusedParams make_params(pt_handle_t h) {
   FusedParams p{};
   p.d = h->d;
   p.Tt = h->Tt; p.T2h = h->T2h; p.Vt = h->Vt; p.Ut = h->Ut;
-  p.t1 = h->t1; p.pphh = h->pphh; p.epsi = h->epsi; p.epsa = h->epsa;
+  p.t1 = h->t1; p.pphh = h->pphh; p.qsum = h->qsum; p.epsi = h->epsi; p.epsa = h->epsa;
   p.orbits = h->d_orbits;
   p.norbits = h->norbits;
   return p;

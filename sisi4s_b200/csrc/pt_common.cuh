@@ -83,6 +83,7 @@ struct FusedParams {
   const int* vslot;    // hole z -> slot of its PPPH slab in Vt; nullptr = identity (all slabs resident)
   const double* t1;    // raw [v,o]
   const double* pphh;  // raw [v,v,o,o]
+  const double* qsum;  // pphh[b,c,j,k] + pphh[c,b,k,j], same layout
   const double* epsi;
   const double* epsa;
   const int4* triples;    // (i,j,k,class) of the sorted triples of this run
@@ -90,7 +91,7 @@ struct FusedParams {
   int norbits;
   int ntriples;
   int order;              // 0: triple-major (orbit fastest), 1: orbit-major (triple fastest; L2 reuse of PPPH tiles)
-  int debug;              // measurement switches: 1 = consumers skip LDS/DMMA (operand-feed ceiling), 2 = skip hole stages' DMMA only
+  int debug;              // measurement switches (wrong results): 1 = consumers skip LDS/DMMA (operand-feed ceiling), 4 = skip the scatter, 8 = skip the epilogue point loops
   long long nitems;       // ntriples * norbits
   double* e_triple;       // [ntriples], accumulated with atomicAdd
 };
@@ -116,6 +117,7 @@ cudaError_t launch_pack_vt_slab(const double* raw_slab, double* vt_slab, Dims d,
 cudaError_t launch_pack_tt(const double* t2, double* tt, Dims d, cudaStream_t s);
 cudaError_t launch_pack_t2h(const double* t2, double* t2h, Dims d, cudaStream_t s);
 cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, cudaStream_t s);
+cudaError_t launch_pphh_symsum(const double* pphh, double* qsum, Dims d, cudaStream_t s);
 cudaError_t launch_ppph_slab_from_vertex(const double* gre, const double* gim, int nf, int np,
                                          int z, double* raw_slab, Dims d, cudaStream_t s);
 

@@ -467,6 +467,12 @@ __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], Pipe& pp
   c.block_h<NEXT_NONE, 1>(acc, hB, uf, fA, hA, un);
 }
 
+// composition table of Permutation<3> indices: S3_MUL[mu][nu] = index of m -> mu(nu(m)), i.e.
+// (x o mu) o nu = x o S3_MUL[mu][nu] (images p0..p5 = 012, 102, 120, 021, 201, 210; this is the
+// `nbr` table of the generic orbit class, checked by static_assert-free tests/test_tables.py)
+__device__ constexpr int8_t S3_MUL[6][6] = {{0, 1, 2, 3, 4, 5}, {1, 0, 3, 2, 5, 4}, {2, 5, 4, 1, 0, 3},
+                                            {3, 4, 5, 0, 1, 2}, {4, 3, 0, 5, 2, 1}, {5, 2, 1, 4, 3, 0}};
+
 __host__ __device__ constexpr int bitswap13(int v) { return (v & 5) | ((v & 2) << 2) | ((v & 8) >> 2); }
 __host__ __device__ constexpr int csel3(int a, int b, int c, int idx) { return idx == 0 ? a : (idx == 1 ? b : c); }
 
@@ -553,28 +559,33 @@ __device__ __forceinline__ void epi_stage_load(const FusedParams& p, const PtCla
   const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
   const int u = tid & 15, w_ = tid >> 4;
   const double* P = p.pphh;
+  const double* S = p.qsum;  // P[b,c,j,k] + P[c,b,k,j]
   const size_t vv = (size_t)v;
   sq0 = sq1 = sq2 = 0.0;
+  if (p.debug & 32) return;  // measurement switch: no global loads in the epilogue (wrong results)
+  // ONE load per operand and no arithmetic on the loaded values here: the results stay in flight
+  // until the staging store, across the barriers in between.  Both hole permutations of a pair
+  // distinct -> the pre-added Qsum, else the one raw entry that exists.
+  auto pick = [&](int both, int m1, int m2, size_t r, size_t c, int h1, int h2) -> const double* {
+    if ((pm & both) == both) return S + r + vv * (c + vv * (h1 + (size_t)o * h2));
+    if (pm & m1) return P + r + vv * (c + vv * (h1 + (size_t)o * h2));
+    if (pm & m2) return P + c + vv * (r + vv * (h2 + (size_t)o * h1));
+    return nullptr;
+  };
   {
     const size_t g1 = gb0 + u, g2 = gc0 + w_;
-    if (g1 < vv && g2 < vv) {
-      if (pm & 1) sq0 += __ldg(P + g1 + vv * (g2 + vv * (hj + (size_t)o * hk)));
-      if (pm & 8) sq0 += __ldg(P + g2 + vv * (g1 + vv * (hk + (size_t)o * hj)));
-    }
+    const double* q = pick(1 | 8, 1, 8, g1, g2, hj, hk);
+    if (q && g1 < vv && g2 < vv) sq0 = __ldg(q);
   }
   {
     const size_t g0 = ga0 + u, g2 = gc0 + w_;
-    if (g0 < vv && g2 < vv) {
-      if (pm & 2) sq1 += __ldg(P + g0 + vv * (g2 + vv * (hi + (size_t)o * hk)));
-      if (pm & 4) sq1 += __ldg(P + g2 + vv * (g0 + vv * (hk + (size_t)o * hi)));
-    }
+    const double* q = pick(2 | 4, 2, 4, g0, g2, hi, hk);
+    if (q && g0 < vv && g2 < vv) sq1 = __ldg(q);
   }
   {
     const size_t g0 = ga0 + u, g1 = gb0 + w_;
-    if (g0 < vv && g1 < vv) {
-      if (pm & 16) sq2 += __ldg(P + g0 + vv * (g1 + vv * (hi + (size_t)o * hj)));
-      if (pm & 32) sq2 += __ldg(P + g1 + vv * (g0 + vv * (hj + (size_t)o * hi)));
-    }
+    const double* q = pick(16 | 32, 16, 32, g0, g1, hi, hj);
+    if (q && g0 < vv && g1 < vv) sq2 = __ldg(q);
   }
   if (tid < 48) {
     const int which = tid >> 4, uu = tid & 15;
@@ -690,7 +701,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       // the halves of a step target different X tiles except in orbits with coinciding
       // ranges; only then (or for very short steps) are the two scatters separated by barriers
       const bool sync = step_sync_always || (st.h[0].en && st.h[1].en && st.h[0].tau == st.h[1].tau);
-      if (!sync) {
+      if (p.debug & 4) {
+        // measurement switch: drop the scatter (results are wrong), keeps the accumulators alive
+        if (acc[0][0][0][0] == 1.2345e300) my_stg[tid] = acc[1][3][1][1];
+      } else if (!sync) {
         if (hf.en) scatter_add(my_stg, tmem_lane_base, acc, hf.tau, hf.q0, hf.q1, grp, wq, lane);
       } else {
         if (grp == 0 && hf.en) scatter_add(my_stg, tmem_lane_base, acc, hf.tau, hf.q0, hf.q1, grp, wq, lane);
@@ -702,6 +716,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
         consumer_barrier();
         tmem_fence_after();
       }
+    }
+
+    // ---- epilogue: E_item = sum_tiles sum_x (Xd + Sd)[x] * (sum_nu c_nu Xd[x o nu]) / D[x]
+    const double e3 = p.epsi[hi] + p.epsi[hj] + p.epsi[hk];
+    const int pm = tab.pmask;
+    double e_acc = 0.0;
+    const bool sym = tab.ntiles == 6 && !(p.debug & 16);   // generic orbit A > B > C: symmetric epilogue
+    // Staging values (singles-term operands, T1 columns, eigenvalues) come from global memory with
+    // DRAM latency.  Generic orbit: all six tiles' values are fetched into registers here, before
+    // the X copy, so the latency hides behind the copy and phase 1; otherwise one tile ahead.
+    double sq[6][3], stv[6][2];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      stv[u][0] = stv[u][1] = 0.0;
+      if (u == 0 || sym)
+        epi_stage_load(p, tab, ob, u, hi, hj, hk, pm, tid, sq[u][0], sq[u][1], sq[u][2], stv[u][0], stv[u][1]);
     }
 
     // ---- X tiles: TMEM -> shared memory (over the drained ring), and clear them for the next item
@@ -728,70 +758,135 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       tmem_wait_st();
     }
 
-    // ---- epilogue: E_item = sum_tiles sum_x (Xd + Sd)[x] * (sum_nu c_nu Xd[x o nu]) / D[x]
-    const double e3 = p.epsi[hi] + p.epsi[hj] + p.epsi[hk];
-    const int pm = tab.pmask;
-    double e_acc = 0.0;
-    // staging values of one tile (singles term operands + eigenvalues), prefetched into
-    // registers one tile ahead so that the global-load latency hides behind the point loop
-    double sq0, sq1, sq2, stv0 = 0.0, stv1 = 0.0;
-    epi_stage_load(p, tab, ob, 0, hi, hj, hk, pm, tid, sq0, sq1, sq2, stv0, stv1);
-    // (the barrier that publishes Xs is the first one inside the tile loop)
-    for (int tl = 0; tl < tab.ntiles; ++tl) {
-      const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
-      const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
-      const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
-      Qs[tid] = sq0;
-      Qs[256 + tid] = sq1;
-      Qs[512 + tid] = sq2;
+
+    const double c0 = tab.coef[0], c1 = tab.coef[1], c2 = tab.coef[2], c3 = tab.coef[3], c4 = tab.coef[4],
+                 c5 = tab.coef[5];
+    const int x0 = tid & 15, x1 = tid >> 4;
+    // xt_index(a,b,c) = (a ^ b ^ s(c)) + 16 b + 256 c with s = bitswap13 (XOR-linear): the six
+    // permuted reads share three low nibbles, each a per-thread constant XOR a function of x2
+    const int l01 = x0 ^ x1, l25 = x1 ^ bitswap13(x0), l34 = x0 ^ bitswap13(x1);
+    auto put_stage = [&](double* Qb, double* tb, const double (&q)[3], const double (&t)[2]) {
+      Qb[tid] = q[0];
+      Qb[256 + tid] = q[1];
+      Qb[512 + tid] = q[2];
       if (tid < 48) {
-        tv[tid] = stv0;
-        tv[48 + tid] = stv1;
+        tb[tid] = t[0];
+        tb[48 + tid] = t[1];
       }
-      consumer_barrier();
-      if (tl + 1 < tab.ntiles) epi_stage_load(p, tab, ob, tl + 1, hi, hj, hk, pm, tid, sq0, sq1, sq2, stv0, stv1);
-      const double* Xt = Xs + tl * XT_DBL;
-      const int8_t* nb = tab.nbr[tl];
-      const double* X1 = Xs + nb[1] * XT_DBL;
-      const double* X2 = Xs + nb[2] * XT_DBL;
-      const double* X3 = Xs + nb[3] * XT_DBL;
-      const double* X4 = Xs + nb[4] * XT_DBL;
-      const double* X5 = Xs + nb[5] * XT_DBL;
-      const double c0 = tab.coef[0], c1 = tab.coef[1], c2 = tab.coef[2], c3 = tab.coef[3], c4 = tab.coef[4],
-                   c5 = tab.coef[5];
-      const int x0 = tid & 15, x1 = tid >> 4;
-      const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
-      const double d01 = e3 - tv[48 + x0] - tv[64 + x1];
-      const double t0 = 0.5 * tv[x0], t1v = 0.5 * tv[16 + x1];
-      const double q2c = 0.5 * Qs[512 + x0 + 16 * x1];
-      // xt_index(a,b,c) = (a ^ b ^ s(c)) + 16 b + 256 c with s = bitswap13 (XOR-linear): the six
-      // permuted reads share three low nibbles, each a per-thread constant XOR a function of x2
-      const int l01 = x0 ^ x1, l25 = x1 ^ bitswap13(x0), l34 = x0 ^ bitswap13(x1);
-      const double* P0 = Xt + 16 * x1;
-      const double* P1 = X1 + 16 * x0;
-      const double* P2 = X2 + 256 * x0;
-      const double* P3 = X3 + 256 * x1;
-      const double* P4 = X4 + 16 * x0 + 256 * x1;
-      const double* P5 = X5 + 16 * x1 + 256 * x0;
-      const double* Q0 = Qs + x1;
-      const double* Q1 = Qs + 256 + x0;
-      const int nv2 = min(16, v - gc0);   // valid x2 of this tile (>= 1)
+    };
+
+    if (p.debug & 8) {
+      // measurement switch: no point loops
+    } else if (sym) {
+      // ================= generic orbit: the six tiles are the images of tile 0 under S3 =================
+      // two staging buffers: the Qs/tv area and the (now free) tail of the scatter staging tiles
+      double* const Qb[2] = {Qs, Xs + 6 * XT_DBL};
+      double* const tb[2] = {tv, Xs + 6 * XT_DBL + 768};
+      put_stage(Qb[0], tb[0], sq[0], stv[0]);
+      consumer_barrier();  // publishes Xs and tile 0's staging values
+      if (!(p.debug & 64)) {
+        // ---- phase 1.  D is symmetric, so the point orbit {x o mu} is handled at once: six reads
+        // v_pi = Xd[x o pi] (one per tile), Z_mu = sum_nu c_nu v_{mu nu}, ONE reciprocal, the Xd.Z/D
+        // part of all six points, and Y[x o mu] = Z_mu / D written back over Xd for the singles part.
+        const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[0][0]);
+        const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[0][1]);
+        const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[0][2]);
+        const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
+        const int nv2 = min(16, v - gc0);
+        const double d01 = e3 - tv[48 + x0] - tv[64 + x1];
+        double* R0 = Xs + 16 * x1;
+        double* R1 = Xs + 1 * XT_DBL + 16 * x0;
+        double* R2 = Xs + 2 * XT_DBL + 256 * x0;
+        double* R3 = Xs + 3 * XT_DBL + 256 * x1;
+        double* R4 = Xs + 4 * XT_DBL + 16 * x0 + 256 * x1;
+        double* R5 = Xs + 5 * XT_DBL + 16 * x1 + 256 * x0;
+        const double cf[6] = {c0, c1, c2, c3, c4, c5};
 #pragma unroll
-      for (int x2 = 0; x2 < 16; ++x2) {
-        // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}; nbr[tl][0] == tl (identity)
-        const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
-        const double xd = P0[a01 + 256 * x2];
-        double zn = c0 * xd;
-        zn += c1 * P1[a01 + 256 * x2];
-        zn += c2 * P2[a25 + 16 * x2];
-        zn += c3 * P3[a34 + 16 * x2];
-        zn += c4 * P4[a34];
-        zn += c5 * P5[a25];
-        const double sd = t0 * Q0[16 * x2] + t1v * Q1[16 * x2] + tv[32 + x2] * q2c;
-        const double dd = d01 - tv[80 + x2];
-        if (valid01 && x2 < nv2) e_acc += (xd + sd) * zn / dd;
+        for (int x2 = 0; x2 < 16; ++x2) {
+          const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
+          double* A[6] = {R0 + a01 + 256 * x2, R1 + a01 + 256 * x2, R2 + a25 + 16 * x2,
+                          R3 + a34 + 16 * x2, R4 + a34, R5 + a25};
+          double vv[6];
+#pragma unroll
+          for (int n = 0; n < 6; ++n) vv[n] = *A[n];
+          const double rd = 1.0 / (d01 - tv[80 + x2]);
+          double dot = 0.0;
+#pragma unroll
+          for (int mu = 0; mu < 6; ++mu) {
+            double z = 0.0;
+#pragma unroll
+            for (int nu = 0; nu < 6; ++nu) z += cf[nu] * vv[S3_MUL[mu][nu]];
+            dot += vv[mu] * z;
+            *A[mu] = z * rd;
+          }
+          if (valid01 && x2 < nv2) e_acc += dot * rd;
+        }
       }
-      consumer_barrier();
+      // ---- phase 2, per tile: singles part sum_x Sd[x] Y[x]; one barrier per tile (ping-pong staging)
+#pragma unroll
+      for (int tl = 0; tl < ((p.debug & 128) ? 0 : 6); ++tl) {
+        consumer_barrier();  // tl = 0: every Y is in place; tl > 0: staging of tile tl is published
+        if (tl + 1 < 6) put_stage(Qb[(tl + 1) & 1], tb[(tl + 1) & 1], sq[(tl + 1) % 6], stv[(tl + 1) % 6]);
+        const double* Qc = Qb[tl & 1];
+        const double* tc = tb[tl & 1];
+        const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
+        const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
+        const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
+        const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
+        const int nv2 = min(16, v - gc0);
+        const double t0 = 0.5 * tc[x0], t1v = 0.5 * tc[16 + x1];
+        const double q2c = 0.5 * Qc[512 + x0 + 16 * x1];
+        const double* Q0 = Qc + x1;
+        const double* Q1 = Qc + 256 + x0;
+        const double* P0 = Xs + tl * XT_DBL + 16 * x1;
+#pragma unroll
+        for (int x2 = 0; x2 < 16; ++x2) {
+          const int a01 = l01 ^ bitswap13(x2);
+          const double sd = t0 * Q0[16 * x2] + t1v * Q1[16 * x2] + tc[32 + x2] * q2c;
+          if (valid01 && x2 < nv2) e_acc += sd * P0[a01 + 256 * x2];
+        }
+      }
+    } else {
+      // ================= degenerate orbits (<= 3 tiles): per tile, six permuted reads per point =================
+      double q[3] = {sq[0][0], sq[0][1], sq[0][2]}, t[2] = {stv[0][0], stv[0][1]};
+      for (int tl = 0; tl < tab.ntiles; ++tl) {
+        const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
+        const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
+        const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
+        put_stage(Qs, tv, q, t);
+        consumer_barrier();
+        if (tl + 1 < tab.ntiles) epi_stage_load(p, tab, ob, tl + 1, hi, hj, hk, pm, tid, q[0], q[1], q[2], t[0], t[1]);
+        const int8_t* nb = tab.nbr[tl];
+        const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
+        const double d01 = e3 - tv[48 + x0] - tv[64 + x1];
+        const double t0 = 0.5 * tv[x0], t1v = 0.5 * tv[16 + x1];
+        const double q2c = 0.5 * Qs[512 + x0 + 16 * x1];
+        const double* Q0 = Qs + x1;
+        const double* Q1 = Qs + 256 + x0;
+        const int nv2 = min(16, v - gc0);   // valid x2 of this tile (>= 1)
+        const double* P0 = Xs + tl * XT_DBL + 16 * x1;
+        const double* P1 = Xs + nb[1] * XT_DBL + 16 * x0;
+        const double* P2 = Xs + nb[2] * XT_DBL + 256 * x0;
+        const double* P3 = Xs + nb[3] * XT_DBL + 256 * x1;
+        const double* P4 = Xs + nb[4] * XT_DBL + 16 * x0 + 256 * x1;
+        const double* P5 = Xs + nb[5] * XT_DBL + 16 * x1 + 256 * x0;
+#pragma unroll
+        for (int x2 = 0; x2 < 16; ++x2) {
+          // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}; nbr[tl][0] == tl (identity)
+          const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
+          const double xd = P0[a01 + 256 * x2];
+          double zn = c0 * xd;
+          zn += c1 * P1[a01 + 256 * x2];
+          zn += c2 * P2[a25 + 16 * x2];
+          zn += c3 * P3[a34 + 16 * x2];
+          zn += c4 * P4[a34];
+          zn += c5 * P5[a25];
+          const double sd = t0 * Q0[16 * x2] + t1v * Q1[16 * x2] + tv[32 + x2] * q2c;
+          const double dd = d01 - tv[80 + x2];
+          if (valid01 && x2 < nv2) e_acc += (xd + sd) * zn / dd;
+        }
+        consumer_barrier();
+      }
     }
     // warp-shuffle reduction, then one atomic per item
 #pragma unroll

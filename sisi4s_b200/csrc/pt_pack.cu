@@ -113,66 +113,116 @@ __global__ void __launch_bounds__(256) pack_ut_kernel(const double* __restrict__
   dst[1] = make_double2(out[2], out[3]);
 }
 
+// Qsum[b,c,j,k] = Vpphh[b,c,j,k] + Vpphh[c,b,k,j]: the two singles-term operands that the distinct
+// hole permutations (j,k) and (k,j) contribute to one point (getSinglesContribution,
+// CcsdPerturbativeTriples.cxx:81-85, summed as in :209-211), pre-added once so that the fused
+// epilogue fetches ONE value per operand.  Same column-major layout as the raw tensor.
+__global__ void __launch_bounds__(256) pphh_symsum_kernel(const double* __restrict__ pphh,
+                                                          double* __restrict__ qsum, Dims d) {
+  __shared__ double tile[32][33];
+  // block: 32 x 32 (b, c) patch of one (j, k) pair; the transposed patch of (k, j) is read coalesced too
+  const int v = d.v, o = d.o;
+  const int nb = (v + 31) / 32;
+  const int pb = blockIdx.x % nb, pc = blockIdx.x / nb;
+  const int j = blockIdx.y, k = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const size_t vv = (size_t)v;
+  const double* T = pphh + vv * vv * ((size_t)k + (size_t)o * j);  // [c,b,k,j]: transposed source
+  const double* S = pphh + vv * vv * ((size_t)j + (size_t)o * k);
+  double* Q = qsum + vv * vv * ((size_t)j + (size_t)o * k);
+  for (int r = ty; r < 32; r += 8) {
+    const int c = 32 * pc + tx, b = 32 * pb + r;  // element T[c + v*b]
+    tile[r][tx] = (c < v && b < v) ? T[c + vv * b] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int b = 32 * pb + tx, c = 32 * pc + r;
+    if (b < v && c < v) Q[b + vv * c] = S[b + vv * c] + tile[tx][r];
+  }
+}
+
 // PPPH slab z from the Coulomb vertex (reference CoulombIntegralsFromVertex.cxx:430-431,
 // Vabci["abci"] = ReG["Gac"] ReG["Gbi"] + ImG["Gac"] ImG["Gbi"], particles = last v states):
 //   slab[a + v*(b + v*c)] = sum_F G[F,a0+a,a0+c] G[F,a0+b,z]   (Re.Re + Im.Im)
-// G is column-major [F + nf*(p + np*q)].  64x64 output tile, K chunks of 16.
+// G is column-major [F + nf*(p + np*q)], i.e. both operands are K-contiguous.  A GEMM with
+// M = (a,c) pairs, N = b, K = 2 NF on the FP64 tensor pipe: 128 x 64 output tile per CTA, K chunks
+// of 16 staged through shared memory (k-major, padded: conflict-free fragment reads), each of the
+// 8 warps owns 32 x 32 of the tile = 4 x 4 DMMA.8x8x4 accumulators.
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+constexpr int VG_M = 128, VG_N = 64, VG_K = 16;
+
 __global__ void __launch_bounds__(256) ppph_slab_from_vertex_kernel(
     const double* __restrict__ gre, const double* __restrict__ gim, int nf, int np, int z,
     double* __restrict__ slab, Dims d) {
-  __shared__ double As[16][64 + 1];
-  __shared__ double Bs[16][64 + 1];
+  __shared__ double As[VG_K][VG_M + 1];
+  __shared__ double Bs[VG_K][VG_N + 1];
   const int v = d.v, a0 = np - v;
   const long long M = (long long)v * v;  // m = a + v*c
-  const long long m0 = (long long)blockIdx.x * 64;
-  const int n0 = blockIdx.y * 64;        // n = b
-  const int tid = threadIdx.x;
-  const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
-  double acc[4][4] = {};
+  const long long m0 = (long long)blockIdx.x * VG_M;
+  const int n0 = blockIdx.y * VG_N;      // n = b
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[4][4][2] = {};
+  // global -> shared assignment: thread loads k = tid & 15 of rows (tid >> 4) + 16 r
+  const int lk = tid & 15, lr = tid >> 4;
+  size_t arow[VG_M / 16], brow[VG_N / 16];
+  bool aok[VG_M / 16], bok[VG_N / 16];
+#pragma unroll
+  for (int r = 0; r < VG_M / 16; ++r) {
+    const long long m = m0 + lr + 16 * r;
+    aok[r] = m < M;
+    const int a = aok[r] ? (int)(m % v) : 0, c = aok[r] ? (int)(m / v) : 0;
+    arow[r] = (size_t)nf * ((a0 + a) + (size_t)np * (a0 + c));
+  }
+#pragma unroll
+  for (int r = 0; r < VG_N / 16; ++r) {
+    const int b = n0 + lr + 16 * r;
+    bok[r] = b < v;
+    brow[r] = (size_t)nf * ((a0 + (bok[r] ? b : 0)) + (size_t)np * z);
+  }
   for (int part = 0; part < 2; ++part) {
     const double* G = part == 0 ? gre : gim;
-    for (int k0 = 0; k0 < nf; k0 += 16) {
-      // 64 rows x 16 k per operand: thread loads 4 elements of each
+    for (int k0 = 0; k0 < nf; k0 += VG_K) {
+      const bool kok = k0 + lk < nf;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int e = tid + 256 * r;  // 0..1023
-        const int kk = e & 15, row = e >> 4;
-        const int k = k0 + kk;
-        double av = 0.0, bv = 0.0;
-        const long long m = m0 + row;
-        if (k < nf && m < M) {
-          const int a = (int)(m % v), c = (int)(m / v);
-          av = G[k + (size_t)nf * ((a0 + a) + (size_t)np * (a0 + c))];
-        }
-        const int b = n0 + row;
-        if (k < nf && b < v) bv = G[k + (size_t)nf * ((a0 + b) + (size_t)np * z)];
-        As[kk][row] = av;
-        Bs[kk][row] = bv;
-      }
+      for (int r = 0; r < VG_M / 16; ++r) As[lk][lr + 16 * r] = (kok && aok[r]) ? G[arow[r] + k0 + lk] : 0.0;
+#pragma unroll
+      for (int r = 0; r < VG_N / 16; ++r) Bs[lk][lr + 16 * r] = (kok && bok[r]) ? G[brow[r] + k0 + lk] : 0.0;
       __syncthreads();
 #pragma unroll
-      for (int kk = 0; kk < 16; ++kk) {
-        double a4[4], b4[4];
+      for (int ks = 0; ks < VG_K; ks += 4) {
+        double af[4], bf[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { a4[u] = As[kk][tm + u]; b4[u] = Bs[kk][tn + u]; }
+        for (int i = 0; i < 4; ++i) af[i] = As[ks + fk][wm + 8 * i + fr];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int j = 0; j < 4; ++j) bf[j] = Bs[ks + fk][wn + 8 * j + fr];
 #pragma unroll
-          for (int w = 0; w < 4; ++w) acc[u][w] = fma(a4[u], b4[w], acc[u][w]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
       __syncthreads();
     }
   }
+  // C fragment: rows 8i + (lane>>2), columns 8j + 2 (lane&3) + {0,1}
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const long long m = m0 + tm + u;
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + wm + 8 * i + fr;
     if (m >= M) continue;
     const int a = (int)(m % v), c = (int)(m / v);
 #pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int b = n0 + tn + w;
-      if (b < v) slab[a + (size_t)v * (b + (size_t)v * c)] = acc[u][w];
-    }
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int b = n0 + wn + 8 * j + 2 * fk + e;
+        if (b < v) slab[a + (size_t)v * (b + (size_t)v * c)] = acc[i][j][e];
+      }
   }
 }
 
@@ -198,10 +248,16 @@ cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, cudaStream_t 
   pack_ut_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(hhhp, ut, d);
   return cudaGetLastError();
 }
+cudaError_t launch_pphh_symsum(const double* pphh, double* qsum, Dims d, cudaStream_t s) {
+  const int nb = (d.v + 31) / 32;
+  dim3 grid(nb * nb, d.o, d.o);
+  pphh_symsum_kernel<<<grid, 256, 0, s>>>(pphh, qsum, d);
+  return cudaGetLastError();
+}
 cudaError_t launch_ppph_slab_from_vertex(const double* gre, const double* gim, int nf, int np,
                                          int z, double* raw_slab, Dims d, cudaStream_t s) {
   const long long M = (long long)d.v * d.v;
-  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((d.v + 63) / 64));
+  dim3 grid((unsigned)((M + VG_M - 1) / VG_M), (unsigned)((d.v + VG_N - 1) / VG_N));
   ppph_slab_from_vertex_kernel<<<grid, 256, 0, s>>>(gre, gim, nf, np, z, raw_slab, d);
   return cudaGetLastError();
 }

@@ -42,3 +42,20 @@ def test_emulated_fused_flow_matches_oracle(kind, o, v, tile):
         a = O.triple_energy(*inp.args(), ijk)
         b = G.emulate_triple(*inp.args(), ijk, tile=tile)
         assert abs(a - b) <= 1e-11 * max(1.0, abs(a)), (ijk, a, b)
+
+
+def test_generic_orbit_tables_are_the_s3_group_table():
+    """The symmetric epilogue of the fused kernel (generic orbit A>B>C) relies on: tile mu of the
+    orbit holds the points x o mu of tile 0, and nbr[mu][nu] is the index of the composed
+    permutation m -> mu(nu(m)) -- the constant S3_MUL in pt_fused.cu."""
+    import re
+    src = open(os.path.join(ROOT, "sisi4s_b200", "csrc", "pt_fused.cu")).read()
+    m = re.search(r"S3_MUL\[6\]\[6\] = \{(.*?)\};", src, re.S)
+    s3 = [[int(x) for x in row.split(",")] for row in re.findall(r"\{([0-9, ]+)\}", m.group(1))]
+    P = [tuple(p) for p in G.PERM]
+    mul = [[P.index(tuple(P[a][P[b][k]] for k in range(3))) for b in range(6)] for a in range(6)]
+    assert s3 == mul
+    for tc in range(4):
+        t = G.ALL_TABLES[tc][0]
+        assert len(t["tiles"]) == 6
+        assert [list(r) for r in t["nbr"]] == mul
