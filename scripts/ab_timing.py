@@ -7,14 +7,18 @@ import json, os, sys
 sys.path.insert(0, %r)
 from sisi4s_b200 import synthetic as S
 from sisi4s_b200.triples import TriplesEngine
-dbg = [int(x) for x in sys.argv[1].split(",")]
+dbg = [x for x in sys.argv[1].split(",")]
 inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
 with TriplesEngine(40, 300) as eng:
     eng.set_inputs(*inp.args())
     b, e = eng.partition(8, 3)
     eng.run(b, b + 200)
     for d in dbg:
-        eng.set_option("debug", d)
+        # "N" = debug switch N; "key=value" = any other option
+        if "=" in d:
+            k, val = d.split("="); eng.set_option(k, int(val))
+        else:
+            eng.set_option("debug", int(d))
         r = eng.run(b, e)
         print(json.dumps({"lib": os.path.basename(os.environ.get("SISI4S_PT_LIB", "default")), "debug": d,
                           "s_kernel": r.seconds_kernel, "tflops_equiv": r.flops / r.seconds_kernel * 1e-12,

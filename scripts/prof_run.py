@@ -10,10 +10,13 @@ step = len(sys.argv) > 1 and sys.argv[1] == "step"
 b = 5000 if step or len(sys.argv) <= 1 else int(sys.argv[1])
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 order = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+tile_holes = int(sys.argv[4]) if len(sys.argv) > 4 else None
 inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
 with TriplesEngine(40, 300) as eng:
     eng.set_inputs(*inp.args())
     eng.set_option("order", order)
+    if tile_holes is not None:
+        eng.set_option("tile_holes", tile_holes)
     rng = eng.partition(8, n) if step else (b, b + n)
     r = eng.run(*rng)
     print("E", r.energy, "s_kernel", r.seconds_kernel, "TF/s", r.flops / r.seconds_kernel * 1e-12)

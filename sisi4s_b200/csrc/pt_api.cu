@@ -44,6 +44,7 @@ struct PtHandle_ {
   int keep_raw = 0;
   int grid = 0;
   int order = 1;
+  int tile_holes = 4;   // L2 locality: triples are launched grouped by hole blocks of this width (0 = reference order)
   int debug = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -225,6 +226,9 @@ int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
     if (value < 0 || (value > 0 && value < 3)) return fail(PT_ERR_INVALID, "slab_slots %lld (0 = all resident, else >= 3)", (long long)value);
     if (h->Vt) return fail(PT_ERR_INVALID, "slab_slots must be set before the PPPH integrals / vertex");
     h->slab_slots = (int)value;
+  } else if (!strcmp(key, "tile_holes")) {
+    if (value < 0) return fail(PT_ERR_INVALID, "tile_holes %lld", (long long)value);
+    h->tile_holes = (int)value;
   } else if (!strcmp(key, "debug")) {
     h->debug = (int)value;
   } else if (!strcmp(key, "order")) {
@@ -539,6 +543,20 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
     }
     if (h->blocked())
       std::stable_sort(ent.begin(), ent.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+    // L2 locality within a launch: the CTAs that run concurrently take CONSECUTIVE list entries (of
+    // one particle-range orbit), so the list is ordered by hole blocks of width tile_holes: any ~150
+    // consecutive triples then touch ~12-20 PPPH slabs instead of up to o, and their tiles stay in L2.
+    // (E_t is independent of the order; results are scattered back through `where`.)
+    if (h->tile_holes > 1) {
+      const int tb = h->tile_holes;
+      std::stable_sort(ent.begin(), ent.end(), [tb](const Entry& a, const Entry& b) {
+        if (a.key != b.key) return a.key < b.key;
+        const int ka[3] = {a.t.x / tb, a.t.y / tb, a.t.z / tb}, kb[3] = {b.t.x / tb, b.t.y / tb, b.t.z / tb};
+        for (int m = 0; m < 3; ++m)
+          if (ka[m] != kb[m]) return ka[m] < kb[m];
+        return false;
+      });
+    }
     h->stats.seconds_kernel = 0.0;
     if (!ent.empty()) {
       std::vector<int4> list(ent.size());
