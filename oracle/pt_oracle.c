@@ -13,8 +13,9 @@
  * getDoublesContribution are done as blocked GEMMs (the reference delegates them to
  * Cyclops CTF @53ae5daa + BLAS, un-vendored), everything else is literal.
  *
- * PARITY: pinned against oracle/pt_oracle.py (NumPy forms A/B) in
- * tests/test_oracle_c.py; see the header of pt_oracle.py for what pins that.
+ * PARITY: pinned against oracle/pt_oracle.py (NumPy forms A/B) in tests/test_oracle_c.py and,
+ * like them, against the (T) energy the reference records for the UEG test system
+ * (cc4s.correct.out.yaml:166-169) in tests/test_known_answers.py: agreement 3e-12.
  *
  * All arrays column-major in the reference's CTF index order:
  *   T1[a,i] T2[a,b,i,j] Vpphh[a,b,i,j] Vhhhp[i,j,k,a] Vppph[a,b,c,i].

@@ -21,20 +21,22 @@ index strings over column-major tensors.  ``A["abc"] += B["bac"]`` means
 ``A[a,b,c] += B[b,a,c]``; we restate that with ``numpy.einsum`` using the very
 same index strings.
 
-PARITY STATUS: the reference ships no runnable test, golden vector or fixture
-for this path and cannot be built here (needs MPI +
-CTF).  The permutation tables below are pinned against the reference's own
+PARITY STATUS: PINNED by a known answer the reference repository holds.  The
+reference cannot be built here (needs MPI + CTF) and ships no unit test for
+this path, but integration-tests/tests/cc4s/ueg/rs1.0-7occ-26virt/
+cc4s.correct.out.yaml:124-169 records MP2, CCSD and (T) energies of the
+uniform electron gas (rs = 1, 7 occupied / 26 virtual states), a system defined
+by closed formulas.  tests/test_known_answers.py regenerates its inputs
+(oracle/ueg.py, restating UegVertexGenerator.cxx; MP2 agrees to 1e-15),
+converges the CCSD amplitudes (oracle/ccsd.py; CCSD energy agrees to 2e-10,
+the reference converged to 1e-8) and checks forms A and B and the C port
+against the recorded (T) = -0.0063019625641725016: agreement 3e-12.
+Additional pins: the permutation tables against the reference's own
 ``Permutation.hpp`` compiled from /root/reference (oracle/ref_perm_dump.cxx ->
-oracle/_ref/); the energy itself is pinned only by mutual agreement of the
-three independent formulations (A, B, C) the reference contains and, when
-oracle/_ref/pt_ref exists, by the reference's own CcsdPerturbativeTriples.cxx
-compiled against a dense single-process stand-in for the CTF API
-(oracle/ctf_shim/).  Without that binary this oracle is "parity unpinned".
-
-Array convention: NumPy arrays indexed exactly like the CTF tensors,
-T1[a,i], T2[a,b,i,j], Vpphh[a,b,i,j], Vhhhp[i,j,k,a], Vppph[a,b,c,i].
-Memory order is irrelevant here; the C ABI takes them column-major
-(Fortran order), see include/sisi4s_pt.h.
+oracle/_ref/), and mutual agreement of the three formulations (A, B, C) the
+reference contains on unsymmetric random inputs.  The other known answers of
+the reference (H2O, HF molecules) need downloaded input files and are not
+reproduced.
 """
 from __future__ import annotations
 

@@ -110,6 +110,26 @@ def test_config2_o20_v100_matches_golden():
     assert st.kernel_launches > 0 and st.flops_algorithmic == pytest.approx(2 * 20**3 * 100**3 * 120)
 
 
+# ------------------------------------------- known answer held by the reference repository
+def test_ueg_known_answer_of_the_reference():
+    """UEG rs=1.0, 7 occupied / 26 virtual: the CUDA path against the (T) correlation energy the
+    reference records for this system, -0.0063019625641725016
+    (integration-tests/tests/cc4s/ueg/rs1.0-7occ-26virt/cc4s.correct.out.yaml:166-169), on inputs
+    restated from the reference's formulas (oracle/ueg.py) and converged CCSD amplitudes
+    (tests/golden/ueg_rs1_no7_nv26.npz; see tests/test_known_answers.py).  Both reference
+    contracts: PPPH integrals and Coulomb vertex."""
+    from oracle import ueg
+    ref_t = -0.0063019625641725016
+    epsi, epsa, gamma = ueg.make_ueg(7, 26, 1.0)
+    vpphh, vhhhp, vppph = S.integrals_from_vertex(gamma, 7, 26)
+    amps = np.load(os.path.join(os.path.dirname(__file__), "golden", "ueg_rs1_no7_nv26.npz"))
+    for kw in (dict(Vppph=vppph), dict(vertex=gamma)):
+        with TriplesEngine(7, 26) as eng:
+            eng.set_inputs(epsi, epsa, amps["T1"], amps["T2"], vpphh, vhhhp, **kw)
+            res = eng.run()
+        assert abs(res.energy - ref_t) <= ABS_TOL, (res.energy, ref_t)
+
+
 # ----------------------------------------------------------- structural properties
 def test_partition_invariance_and_ranges():
     inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
