@@ -44,7 +44,7 @@ struct PtHandle_ {
   int keep_raw = 0;
   int grid = 0;
   int order = 1;
-  int tile_holes = 4;   // L2 locality: triples are launched grouped by hole blocks of this width (0 = reference order)
+  int tile_holes = 0;   // optional: launch list grouped by hole blocks of this width (0 = reference order; measured: no effect on DRAM traffic, profiles/r01h_step_traffic_th*.csv)
   int debug = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
