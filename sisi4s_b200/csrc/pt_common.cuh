@@ -94,6 +94,8 @@ struct FusedParams {
   int debug;              // measurement switches (wrong results): 1 = consumers skip LDS/DMMA (operand-feed ceiling), 4 = skip the scatter, 8 = skip the epilogue point loops
   long long nitems;       // ntriples * norbits
   double* e_triple;       // [ntriples], accumulated with atomicAdd
+  unsigned int* sync_ctr; // item-round barrier counter (zeroed per launch); nullptr = CTAs run free
+  int sync_every;         // barrier before every sync_every-th item round
 };
 
 // item -> (triple, orbit).  Orbit-major order makes the CTAs that run concurrently work on

@@ -288,7 +288,22 @@ __device__ __forceinline__ void producer_loop(const FusedParams& p, const Pipe& 
   while (ld.valid) {
     if (ld.item != cur_item) {
       // the epilogue of the previous item copies the X tiles over the ring: wait until it is done
-      if (items_started > 0) mbar_wait(go_bar, (items_started - 1) & 1);
+      if (items_started > 0) {
+        mbar_wait(go_bar, (items_started - 1) & 1);
+        // Item-round barrier: no CTA starts its n-th item before every CTA has finished its
+        // (n-1)-th.  Concurrent CTAs work on the same particle-range orbit of neighbouring hole
+        // triples and share two of their three PPPH slabs; kept in step they read the same tiles
+        // within the L2's residency window, which turns most DRAM re-reads into L2 hits.  (All
+        // CTAs are co-resident: cooperative launch, one CTA per SM.)
+        if (p.sync_ctr && items_started % (uint32_t)p.sync_every == 0) {
+          const unsigned target = items_started * gridDim.x;
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.sync_ctr) : "memory");
+            if (seen < target) __nanosleep(200);
+          } while (seen < target);
+        }
+      }
       ++items_started;
       cur_item = ld.item;
     }
@@ -922,6 +937,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
     tmem_fence_after();
     if (tid == 0) {
       mbar_arrive(go_bar);  // Xs has been read by everyone: the producer may refill the ring
+      if (p.sync_ctr) {
+        __threadfence();
+        atomicAdd(p.sync_ctr, 1u);  // this CTA has finished one more item (item-round barrier)
+      }
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < NCONSUMER_WARPS; ++w) s += red[w];
@@ -1004,6 +1023,13 @@ cudaError_t fused_configure(int* smem_bytes_out) {
 
 cudaError_t launch_fused(const FusedParams& p, int grid, cudaStream_t s) {
   if (p.nitems <= 0) return cudaSuccess;
+  if (p.sync_ctr) {
+    // the item-round barrier spins on other CTAs: co-residency must be guaranteed, not assumed
+    FusedParams pc = p;
+    void* args[] = {&pc};
+    return cudaLaunchCooperativeKernel((const void*)pt_fused_kernel, dim3(grid), dim3(FUSED_THREADS), args,
+                                       FUSED_SMEM_BYTES, s);
+  }
   pt_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(p);
   return cudaGetLastError();
 }
