@@ -144,6 +144,24 @@ def test_partition_invariance_and_ranges():
         assert empty.energy == 0.0 and empty.per_triple.size == 0
 
 
+def test_launch_order_options_do_not_change_energies():
+    """Scheduling knobs of the fused kernel (item order, class-sorted / hole-blocked launch list,
+    item-round barrier with cooperative launch, grid size) only reorder independent work."""
+    inp = S.make_inputs(6, 40, seed=4, kind="random")
+    e_ref, per_ref = golden(6, 40, "random", 4)
+    with engine_for(inp) as eng:
+        base = eng.run().per_triple
+        for opts in ({"order": 0}, {"class_sort": 0}, {"tile_holes": 2}, {"item_sync": 1}, {"item_sync": 3},
+                     {"grid": 7}, {"grid": 7, "item_sync": 1}):
+            for k, val in opts.items():
+                eng.set_option(k, val)
+            got = eng.run().per_triple
+            assert np.allclose(got, base, rtol=1e-13, atol=0), opts
+            for k in opts:
+                eng.set_option(k, {"order": 1, "class_sort": 1, "tile_holes": 0, "item_sync": 0, "grid": 0}[k])
+    assert close(float(base.sum()), e_ref, "random")
+
+
 def test_vertex_input_equals_ppph_input():
     """CoulombVertex contract of the compiled reference class (:48-78) == PPPH contract."""
     inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
