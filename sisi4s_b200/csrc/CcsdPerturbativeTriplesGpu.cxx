@@ -201,8 +201,9 @@ void CcsdPerturbativeTriplesGpu::dryRun() {
   DryTensor<> *epsa(getTensorArgument<double, DryTensor<double>>("ParticleEigenEnergies"));
   const double No(epsi->lens[0]), Nv(epsa->lens[0]);
   const double nr(std::ceil(Nv / 16.0));
-  // packed PPPH + two packed copies of T2 + PPHH + one staging slab, all FP64, per GPU
-  const double bytes(8.0 * (No * nr * nr * std::ceil(Nv / 4.0) * 1024.0 + 3.0 * Nv * Nv * No * No
+  // packed PPPH + two packed copies of T2 + PPHH and its pre-added pair sums + one staging slab,
+  // all FP64, per GPU
+  const double bytes(8.0 * (No * nr * nr * std::ceil(Nv / 4.0) * 1024.0 + 4.0 * Nv * Nv * No * No
                             + Nv * Nv * Nv));
   LOG(0, "CcsdPerturbativeTriplesGpu") << "device memory per GPU=" << bytes / 1e9 << " GB" << std::endl;
 }

@@ -345,7 +345,7 @@ class CcsdPerturbativeTriples(Algorithm):
         nr = (v + 15) // 16
         nk4, nl4 = (v + 3) // 4, (o + 3) // 4
         packed = o * nr * nr * nk4 * 1024 + 2 * o * o * nr * 64 * max(nk4, 1) + o * nr * nr * nl4 * 1024
-        raw = v * v * o * o + v * o + v ** 3
+        raw = 2 * v * v * o * o + v * o + v ** 3          # PPHH + its pre-added pair sums, T1, one slab stage
         self.dry_bytes = 8 * (packed + raw)
         return self.dry_bytes
 
