@@ -34,6 +34,25 @@ int fail(int code, const char* fmt, ...) {
                   "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
   } while (0)
 
+// scratch device memory / events of one call: released on every exit path (the CU macro returns early)
+template <typename T>
+struct Scratch {
+  T* p = nullptr;
+  Scratch() = default;
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  ~Scratch() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, n * sizeof(T)); }
+  T* release() { T* q = p; p = nullptr; return q; }
+  operator T*() const { return p; }
+};
+struct ScratchEvent {
+  cudaEvent_t e = nullptr;
+  ~ScratchEvent() { if (e) cudaEventDestroy(e); }
+  cudaError_t create() { return cudaEventCreate(&e); }
+  operator cudaEvent_t() const { return e; }
+};
+
 }  // namespace
 
 struct PtHandle_ {
@@ -297,10 +316,12 @@ int pt_set_doubles(pt_handle_t h, const double* t2) {
   CU(cudaSetDevice(h->device));
   Timer tm(h->ev0, h->ev1, h->stream);
   const size_t n = (size_t)h->d.v * h->d.v * h->d.o * h->d.o;
+  Scratch<double> tmp;
   double* raw = h->t2_raw;
   if (!raw) {
-    CU(cudaMalloc((void**)&raw, n * sizeof(double)));
-    if (h->keep_raw) { h->t2_raw = raw; h->bytes_alloc += (double)(n * sizeof(double)); }
+    CU(tmp.alloc(n));
+    raw = tmp;
+    if (h->keep_raw) { h->t2_raw = tmp.release(); h->bytes_alloc += (double)(n * sizeof(double)); }
   }
   if (int rc = upload(h, raw, t2, n)) return rc;
   if (!h->Tt) CU(h->alloc(&h->Tt, tt_elems(h->d)));
@@ -309,7 +330,6 @@ int pt_set_doubles(pt_handle_t h, const double* t2) {
   CU(launch_pack_t2h(raw, h->T2h, h->d, h->stream));
   h->stats.kernel_launches += 2;
   h->stats.seconds_upload += tm.stop();
-  if (!h->keep_raw) CU(cudaFree(raw));
   h->have_t2 = true;
   return PT_OK;
 }
@@ -319,17 +339,18 @@ int pt_set_hhhp(pt_handle_t h, const double* vijka) {
   CU(cudaSetDevice(h->device));
   Timer tm(h->ev0, h->ev1, h->stream);
   const size_t n = (size_t)h->d.o * h->d.o * h->d.o * h->d.v;
+  Scratch<double> tmp;
   double* raw = h->hhhp_raw;
   if (!raw) {
-    CU(cudaMalloc((void**)&raw, n * sizeof(double)));
-    if (h->keep_raw) { h->hhhp_raw = raw; h->bytes_alloc += (double)(n * sizeof(double)); }
+    CU(tmp.alloc(n));
+    raw = tmp;
+    if (h->keep_raw) { h->hhhp_raw = tmp.release(); h->bytes_alloc += (double)(n * sizeof(double)); }
   }
   if (int rc = upload(h, raw, vijka, n)) return rc;
   if (!h->Ut) CU(h->alloc(&h->Ut, ut_elems(h->d)));
   CU(launch_pack_ut(raw, h->Ut, h->d, h->stream));
   h->stats.kernel_launches += 1;
   h->stats.seconds_upload += tm.stop();
-  if (!h->keep_raw) CU(cudaFree(raw));
   h->have_hhhp = true;
   return PT_OK;
 }
@@ -487,10 +508,9 @@ static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<d
   if (!h->t2_raw || !h->ppph_raw || !h->hhhp_raw)
     return fail(PT_ERR_INVALID, "PT_ENGINE_NAIVE needs option keep_raw=1 set before the tensors");
   const size_t n3 = (size_t)h->d.v * h->d.v * h->d.v;
-  double* w = nullptr;
-  double* d_e = nullptr;
-  CU(cudaMalloc((void**)&w, 6 * n3 * sizeof(double)));
-  CU(cudaMalloc((void**)&d_e, tr.size() * sizeof(double)));
+  Scratch<double> w, d_e;
+  CU(w.alloc(6 * n3));
+  CU(d_e.alloc(tr.size()));
   CU(cudaMemsetAsync(d_e, 0, tr.size() * sizeof(double), h->stream));
   static const int perm[6][3] = {{0, 1, 2}, {1, 0, 2}, {1, 2, 0}, {0, 2, 1}, {2, 0, 1}, {2, 1, 0}};
   for (size_t n = 0; n < tr.size(); ++n) {
@@ -517,8 +537,6 @@ static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<d
   CU(cudaMemcpyAsync(e_out.data(), d_e, tr.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->stats.bytes_d2h += (double)(tr.size() * sizeof(double));
-  CU(cudaFree(w));
-  CU(cudaFree(d_e));
   return PT_OK;
 }
 
@@ -580,15 +598,15 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
     if (!ent.empty()) {
       std::vector<int4> list(ent.size());
       for (size_t n = 0; n < ent.size(); ++n) list[n] = ent[n].t;
-      int4* d_list = nullptr;
-      double* d_e = nullptr;
-      CU(cudaMalloc((void**)&d_list, list.size() * sizeof(int4)));
-      CU(cudaMalloc((void**)&d_e, list.size() * sizeof(double)));
+      Scratch<int4> d_list;
+      Scratch<double> d_e;
+      CU(d_list.alloc(list.size()));
+      CU(d_e.alloc(list.size()));
       CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
       CU(cudaMemsetAsync(d_e, 0, list.size() * sizeof(double), h->stream));
-      cudaEvent_t k0, k1;
-      CU(cudaEventCreate(&k0));
-      CU(cudaEventCreate(&k1));
+      ScratchEvent k0, k1;
+      CU(k0.create());
+      CU(k1.create());
       for (size_t g0 = 0; g0 < ent.size();) {
         size_t g1 = g0;
         while (g1 < ent.size() && ent[g1].key == ent[g0].key) ++g1;
@@ -626,16 +644,12 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
         h->stats.kernel_launches += 1;
         g0 = g1;
       }
-      CU(cudaEventDestroy(k0));
-      CU(cudaEventDestroy(k1));
       std::vector<double> el(list.size());
       CU(cudaMemcpyAsync(el.data(), d_e, list.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
       h->stats.bytes_h2d += (double)(list.size() * sizeof(int4));
       h->stats.bytes_d2h += (double)(list.size() * sizeof(double));
       for (size_t n = 0; n < list.size(); ++n) e[ent[n].where] = el[n];
-      CU(cudaFree(d_list));
-      CU(cudaFree(d_e));
     }
   }
   h->stats.seconds_run = tm.stop();
@@ -665,15 +679,14 @@ int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, 
   const int o = h->d.o, nr = h->d.nr;
   if (x < 0 || y < 0 || z < 0 || x >= o || y >= o || z >= o || ra < 0 || rb < 0 || rc < 0 || ra >= nr || rb >= nr || rc >= nr)
     return fail(PT_ERR_INVALID, "pt_debug_w_tile: index out of range");
-  double* d_out = nullptr;
-  CU(cudaMalloc((void**)&d_out, XT_DBL * sizeof(double)));
+  Scratch<double> d_out;
+  CU(d_out.alloc(XT_DBL));
   FusedParams p = make_params(h);
   WTileJob job{x, y, z, ra, rb, rc};
   CU(launch_w_tile(p, job, d_out, h->stream));
   h->stats.kernel_launches += 1;
   CU(cudaMemcpyAsync(out, d_out, XT_DBL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  CU(cudaFree(d_out));
   return PT_OK;
 }
 
@@ -681,11 +694,11 @@ int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double* 
   if (!h || !tflops) return fail(PT_ERR_INVALID, "pt_bench_fp64: null");
   if (warps_per_sm < 1 || warps_per_sm > 32 || iters < 1) return fail(PT_ERR_INVALID, "pt_bench_fp64: args");
   CU(cudaSetDevice(h->device));
-  double* sink = nullptr;
-  unsigned long long* cyc = nullptr;
+  Scratch<double> sink;
+  Scratch<unsigned long long> cyc;
   const int blocks = h->sm_count;
-  CU(cudaMalloc((void**)&sink, sizeof(double)));
-  CU(cudaMalloc((void**)&cyc, blocks * sizeof(unsigned long long)));
+  CU(sink.alloc(1));
+  CU(cyc.alloc(blocks));
   CU(launch_bench_fp64(mode, blocks, warps_per_sm, iters / 8 + 1, sink, cyc, h->stream));  // warm-up
   CU(cudaStreamSynchronize(h->stream));
   Timer tm(h->ev0, h->ev1, h->stream);
@@ -701,8 +714,6 @@ int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double* 
   const double flops = 2.0 * fma_per_warp_iter * (double)iters * warps_per_sm * blocks;
   *tflops = flops / sec * 1e-12;
   if (sm_mhz_est) *sm_mhz_est = (double)mx / sec * 1e-6;
-  CU(cudaFree(sink));
-  CU(cudaFree(cyc));
   return PT_OK;
 }
 
