@@ -67,6 +67,17 @@ typedef struct PtStats {
 /* o, v: dimensions; device: CUDA ordinal.  Replaces the constructor +
  * sliceTensors() of the reference class (CcsdPerturbativeTriples.cxx:16-79).  */
 int pt_create(pt_handle_t *out, int o, int v, int device);
+/* Engine for a hole SUBSET of a larger problem (out-of-core driver for shapes whose T2 / PPHH
+ * tensors exceed one GPU, BASELINE configs[4]): o_act active holes -- the hole indices i,j,k of
+ * the triples that are run, in ascending order of the full problem -- and o_all holes in the
+ * contraction sum_l of getDoublesContribution (:94).  Shapes then are
+ *   HoleEigenEnergies[o_act], CcsdSinglesAmplitudes[v,o_act], PPHHCoulombIntegrals[v,v,o_act,o_act],
+ *   CcsdDoublesAmplitudes[v,v,o_act,o_act]        (pt_set_doubles: particle term T2[a,d,x,y]),
+ *   CcsdDoublesAmplitudes[v,v,o_act,o_all]        (pt_set_doubles_hole: hole term T2[a,b,x,l]),
+ *   HHHPCoulombIntegrals[o_act,o_act,o_all,v], PPPHCoulombIntegrals[v,v,v,o_act].
+ * The caller slices the full tensors; E_t of a triple is the same number as in the full problem.
+ * pt_create(o, v) == pt_create_ex(o, o, v).  PT_ENGINE_NAIVE needs o_act == o_all.             */
+int pt_create_ex(pt_handle_t *out, int o_act, int o_all, int v, int device);
 int pt_destroy(pt_handle_t h);
 const char *pt_last_error(void);
 const char *pt_version(void);
@@ -90,6 +101,10 @@ int pt_set_eigenenergies(pt_handle_t h, const double *epsi, const double *epsa);
 int pt_set_singles(pt_handle_t h, const double *t1);
 /* CcsdDoublesAmplitudes[v,v,o,o] ("abij")                                     */
 int pt_set_doubles(pt_handle_t h, const double *t2);
+/* pt_create_ex engines only: the doubles amplitudes of the HOLE term, T2[a,b,x,l] with x over
+ * the active and l over all holes, [v,v,o_act,o_all].  (With o_act == o_all pt_set_doubles
+ * serves both terms and this call is not needed.)                              */
+int pt_set_doubles_hole(pt_handle_t h, const double *t2_xl);
 /* PPHHCoulombIntegrals[v,v,o,o] (getSinglesContribution, :81-85)              */
 int pt_set_pphh(pt_handle_t h, const double *vabij);
 /* HHHPCoulombIntegrals[o,o,o,v] (hole term of getDoublesContribution, :94)    */
@@ -124,6 +139,9 @@ int pt_partition(int o, int nranks, int rank, int64_t *begin, int64_t *end);
  * sum; e_per_triple: NULL or end-begin doubles.  The caller adds CcsdEnergy
  * (:241-247) and, across GPUs, all-reduces the scalar.                        */
 int pt_run(pt_handle_t h, int64_t begin, int64_t end, double *e_triples, double *e_per_triple);
+/* Same for an explicit list of n sorted-triple indices (reference enumeration over the ACTIVE
+ * holes), in any order, e.g. the triples of one hole-block triple.  e_per_triple: NULL or n.   */
+int pt_run_list(pt_handle_t h, int64_t n, const int64_t *triples, double *e_triples, double *e_per_triple);
 int pt_get_stats(pt_handle_t h, PtStats *stats);
 
 /* ---- debug / measurement helpers (not part of the drop-in contract) ------- */

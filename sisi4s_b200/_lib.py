@@ -38,6 +38,7 @@ _DP = C.POINTER(C.c_double)
 _H = C.c_void_p
 SYMBOLS = {
     "pt_create": (C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int]),
+    "pt_create_ex": (C.c_int, [C.POINTER(_H), C.c_int, C.c_int, C.c_int, C.c_int]),
     "pt_destroy": (C.c_int, [_H]),
     "pt_last_error": (C.c_char_p, []),
     "pt_version": (C.c_char_p, []),
@@ -45,6 +46,7 @@ SYMBOLS = {
     "pt_set_eigenenergies": (C.c_int, [_H, _DP, _DP]),
     "pt_set_singles": (C.c_int, [_H, _DP]),
     "pt_set_doubles": (C.c_int, [_H, _DP]),
+    "pt_set_doubles_hole": (C.c_int, [_H, _DP]),
     "pt_set_pphh": (C.c_int, [_H, _DP]),
     "pt_set_hhhp": (C.c_int, [_H, _DP]),
     "pt_set_ppph_slabs": (C.c_int, [_H, C.c_int, C.c_int, _DP]),
@@ -53,6 +55,7 @@ SYMBOLS = {
     "pt_num_triples": (C.c_int64, [C.c_int]),
     "pt_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "pt_run": (C.c_int, [_H, C.c_int64, C.c_int64, _DP, _DP]),
+    "pt_run_list": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_int64), _DP, _DP]),
     "pt_get_stats": (C.c_int, [_H, C.POINTER(PtStats)]),
     "pt_debug_w_tile": (C.c_int, [_H] + [C.c_int] * 6 + [_DP]),
     "pt_bench_fp64": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, _DP, _DP]),

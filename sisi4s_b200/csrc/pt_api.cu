@@ -90,6 +90,7 @@ struct PtHandle_ {
   const double* host_ppph = nullptr;        // caller-owned PPPHCoulombIntegrals[v,v,v,o]
   int nslots() const { return (slab_slots > 0 && slab_slots < d.o) ? slab_slots : d.o; }
   bool blocked() const { return nslots() < d.o; }
+  bool have_t2h = false;
   bool have_eps = false, have_t1 = false, have_t2 = false, have_pphh = false, have_hhhp = false;
   // work lists
   uchar4* d_orbits = nullptr;
@@ -174,8 +175,10 @@ int pt_partition(int o, int nranks, int rank, int64_t* begin, int64_t* end) {
   return PT_OK;
 }
 
-int pt_create(pt_handle_t* out, int o, int v, int device) {
-  if (!out || o < 1 || v < 1) return fail(PT_ERR_INVALID, "pt_create: need o>=1, v>=1");
+int pt_create(pt_handle_t* out, int o, int v, int device) { return pt_create_ex(out, o, o, v, device); }
+
+int pt_create_ex(pt_handle_t* out, int o, int o_all, int v, int device) {
+  if (!out || o < 1 || v < 1 || o_all < o) return fail(PT_ERR_INVALID, "pt_create: need 1 <= o_act <= o_all, v >= 1");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -189,7 +192,7 @@ int pt_create(pt_handle_t* out, int o, int v, int device) {
     return fail(PT_ERR_UNSUPPORTED, "pt_create: device sm_%d%d, built for sm_100a only", prop.major,
                 prop.minor);
   pt_handle_t h = new PtHandle_();
-  h->d = make_dims(o, v);
+  h->d = make_dims(o, v, o_all);
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->stats.sm_count = prop.multiProcessorCount;
@@ -325,12 +328,32 @@ int pt_set_doubles(pt_handle_t h, const double* t2) {
   }
   if (int rc = upload(h, raw, t2, n)) return rc;
   if (!h->Tt) CU(h->alloc(&h->Tt, tt_elems(h->d)));
-  if (!h->T2h) CU(h->alloc(&h->T2h, t2h_elems(h->d)));
   CU(launch_pack_tt(raw, h->Tt, h->d, h->stream));
-  CU(launch_pack_t2h(raw, h->T2h, h->d, h->stream));
-  h->stats.kernel_launches += 2;
+  h->stats.kernel_launches += 1;
+  if (h->d.ol == h->d.o) {  // the same tensor serves the hole term
+    if (!h->T2h) CU(h->alloc(&h->T2h, t2h_elems(h->d)));
+    CU(launch_pack_t2h(raw, h->T2h, h->d, h->stream));
+    h->stats.kernel_launches += 1;
+    h->have_t2h = true;
+  }
   h->stats.seconds_upload += tm.stop();
   h->have_t2 = true;
+  return PT_OK;
+}
+
+int pt_set_doubles_hole(pt_handle_t h, const double* t2_xl) {
+  if (!h || !t2_xl) return fail(PT_ERR_INVALID, "pt_set_doubles_hole: null");
+  CU(cudaSetDevice(h->device));
+  Timer tm(h->ev0, h->ev1, h->stream);
+  const size_t n = (size_t)h->d.v * h->d.v * h->d.o * h->d.ol;   // [v,v,o_act,o_all]
+  Scratch<double> raw;
+  CU(raw.alloc(n));
+  if (int rc = upload(h, raw, t2_xl, n)) return rc;
+  if (!h->T2h) CU(h->alloc(&h->T2h, t2h_elems(h->d)));
+  CU(launch_pack_t2h(raw, h->T2h, h->d, h->stream));
+  h->stats.kernel_launches += 1;
+  h->stats.seconds_upload += tm.stop();   // synchronises: raw may be released
+  h->have_t2h = true;
   return PT_OK;
 }
 
@@ -338,7 +361,7 @@ int pt_set_hhhp(pt_handle_t h, const double* vijka) {
   if (!h || !vijka) return fail(PT_ERR_INVALID, "pt_set_hhhp: null");
   CU(cudaSetDevice(h->device));
   Timer tm(h->ev0, h->ev1, h->stream);
-  const size_t n = (size_t)h->d.o * h->d.o * h->d.o * h->d.v;
+  const size_t n = (size_t)h->d.o * h->d.o * h->d.ol * h->d.v;   // [o,o,o_all,v]
   Scratch<double> tmp;
   double* raw = h->hhhp_raw;
   if (!raw) {
@@ -487,6 +510,7 @@ static int check_inputs(pt_handle_t h) {
   if (!h->have_eps) return fail(PT_ERR_MISSING, "Missing argument: HoleEigenEnergies/ParticleEigenEnergies");
   if (!h->have_t1) return fail(PT_ERR_MISSING, "Missing argument: CcsdSinglesAmplitudes");
   if (!h->have_t2) return fail(PT_ERR_MISSING, "Missing argument: CcsdDoublesAmplitudes");
+  if (!h->have_t2h) return fail(PT_ERR_MISSING, "Missing argument: CcsdDoublesAmplitudes (hole term, pt_set_doubles_hole)");
   if (!h->have_pphh) return fail(PT_ERR_MISSING, "Missing argument: PPHHCoulombIntegrals");
   if (!h->have_hhhp) return fail(PT_ERR_MISSING, "Missing argument: HHHPCoulombIntegrals");
   for (int k = 0; k < h->d.o; ++k)
@@ -507,6 +531,7 @@ static FusedParams make_params(pt_handle_t h) {
 static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<double>& e_out) {
   if (!h->t2_raw || !h->ppph_raw || !h->hhhp_raw)
     return fail(PT_ERR_INVALID, "PT_ENGINE_NAIVE needs option keep_raw=1 set before the tensors");
+  if (h->d.ol != h->d.o) return fail(PT_ERR_UNSUPPORTED, "PT_ENGINE_NAIVE needs o_act == o_all");
   const size_t n3 = (size_t)h->d.v * h->d.v * h->d.v;
   Scratch<double> w, d_e;
   CU(w.alloc(6 * n3));
@@ -540,6 +565,9 @@ static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<d
   return PT_OK;
 }
 
+// the triples `tr` (any order) -> e[n]; shared by pt_run and pt_run_list
+static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_triples, double* e_per_triple);
+
 int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double* e_per_triple) {
   if (!h || !e_triples) return fail(PT_ERR_INVALID, "pt_run: null");
   CU(cudaSetDevice(h->device));
@@ -549,6 +577,25 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
   if (begin < 0 || end > (int64_t)all.size() || begin > end)
     return fail(PT_ERR_INVALID, "pt_run: triple range [%lld,%lld) of %zu", (long long)begin, (long long)end, all.size());
   std::vector<Triple> tr(all.begin() + begin, all.begin() + end);
+  return run_triples(h, tr, e_triples, e_per_triple);
+}
+
+int pt_run_list(pt_handle_t h, int64_t n, const int64_t* triples, double* e_triples, double* e_per_triple) {
+  if (!h || !e_triples || n < 0 || (n > 0 && !triples)) return fail(PT_ERR_INVALID, "pt_run_list: null");
+  CU(cudaSetDevice(h->device));
+  if (int rc = check_inputs(h)) return rc;
+  std::vector<Triple> all;
+  enumerate_triples(h->d.o, all);
+  std::vector<Triple> tr((size_t)n);
+  for (int64_t m = 0; m < n; ++m) {
+    if (triples[m] < 0 || triples[m] >= (int64_t)all.size())
+      return fail(PT_ERR_INVALID, "pt_run_list: triple %lld of %zu", (long long)triples[m], all.size());
+    tr[(size_t)m] = all[(size_t)triples[m]];
+  }
+  return run_triples(h, tr, e_triples, e_per_triple);
+}
+
+static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_triples, double* e_per_triple) {
   std::vector<double> e(tr.size(), 0.0);
   Timer tm(h->ev0, h->ev1, h->stream);
   long long weight = 0;
@@ -659,7 +706,7 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
   for (double x : e) sum += (long double)x;
   *e_triples = (double)sum;
   if (e_per_triple) std::copy(e.begin(), e.end(), e_per_triple);
-  const double o = h->d.o, v = h->d.v;
+  const double o = h->d.ol, v = h->d.v;
   h->stats.flops_algorithmic = 2.0 * v * v * v * (v + o) * (double)weight;
   h->stats.triples_run = (int64_t)tr.size();
   return PT_OK;

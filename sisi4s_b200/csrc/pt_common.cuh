@@ -8,7 +8,7 @@
 //
 //   TILE = 16 particle indices per range, nr = ceil(v/16) ranges, vp = 16 nr
 //   nk4 = ceil(v/4) chunks of the particle contraction index d
-//   nl4 = ceil(o/4) chunks of the hole contraction index l
+//   nl4 = ceil(ol/4) chunks of the hole contraction index l (ol = o unless pt_create_ex)
 //
 //   Vt [z][Q][R][dc][n=256][kk=4]      = Vppph[b=16Q+n/16, c=16R+n%16, d=4dc+kk, z]
 //   Tt [y][x][P][dc][m=16][kk=4]       = T2[a=16P+m, d=4dc+kk, x, y]
@@ -37,20 +37,23 @@ constexpr int NPRODUCER_WARPS = 4;          // stage j of the operand stream is 
 constexpr int FUSED_THREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
 
 struct Dims {
-  int o, v;
+  int o, v;  // ACTIVE holes (the hole indices of the triples that are run), particles
+  int ol;    // holes of the contraction sum_l of getDoublesContribution; = o unless the engine holds a
+             // hole SUBSET of a larger problem (pt_create_ex)
   int nr;    // particle ranges
   int vp;    // 16*nr
   int nk4;   // ceil(v/4)
   int nl4;   // ceil(o/4)
 };
 
-__host__ __device__ inline Dims make_dims(int o, int v) {
+__host__ __device__ inline Dims make_dims(int o, int v, int ol = 0) {
   Dims d;
   d.o = o; d.v = v;
+  d.ol = ol > 0 ? ol : o;
   d.nr = (v + TILE - 1) / TILE;
   d.vp = d.nr * TILE;
   d.nk4 = (v + 3) / 4;
-  d.nl4 = (o + 3) / 4;
+  d.nl4 = (d.ol + 3) / 4;
   return d;
 }
 

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) pack_tt_kernel(const double* __restrict__
   dst[1] = make_double2(out[2], out[3]);
 }
 
-// T2h[x][P][Q][lc][g][b8][m][kk] = T2[a=16P+m, b=16Q+8g+b8, x, l=4lc+kk]
+// T2h[x][P][Q][lc][g][b8][m][kk] = T2[a=16P+m, b=16Q+8g+b8, x, l=4lc+kk]   (raw [v,v,o,ol]: x active, l all)
 __global__ void __launch_bounds__(256) pack_t2h_kernel(const double* __restrict__ t2,
                                                        double* __restrict__ t2h, Dims d) {
   const size_t rows = (size_t)d.o * d.nr * d.nr * d.nl4 * 256;
@@ -81,14 +81,14 @@ __global__ void __launch_bounds__(256) pack_t2h_kernel(const double* __restrict_
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const int l = 4 * lc + kk;
-    out[kk] = (a < d.v && b < d.v && l < d.o) ? t2[a + v * (b + v * (x + (size_t)d.o * l))] : 0.0;
+    out[kk] = (a < d.v && b < d.v && l < d.ol) ? t2[a + v * (b + v * (x + (size_t)d.o * l))] : 0.0;
   }
   double2* dst = reinterpret_cast<double2*>(t2h + gid * 4);
   dst[0] = make_double2(out[0], out[1]);
   dst[1] = make_double2(out[2], out[3]);
 }
 
-// Ut[z][y][R][lc][c][kk] = -Vhhhp[y, z, l=4lc+kk, c=16R+c]
+// Ut[z][y][R][lc][c][kk] = -Vhhhp[y, z, l=4lc+kk, c=16R+c]   (raw [o,o,ol,v])
 __global__ void __launch_bounds__(256) pack_ut_kernel(const double* __restrict__ hhhp,
                                                       double* __restrict__ ut, Dims d) {
   const size_t rows = (size_t)d.o * d.o * d.nr * d.nl4 * 16;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) pack_ut_kernel(const double* __restrict__
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const int l = 4 * lc + kk;
-    out[kk] = (c < d.v && l < d.o) ? -hhhp[y + o * (z + o * (l + o * c))] : 0.0;
+    out[kk] = (c < d.v && l < d.ol) ? -hhhp[y + o * (z + o * (l + (size_t)d.ol * c))] : 0.0;
   }
   double2* dst = reinterpret_cast<double2*>(ut + gid * 4);
   dst[0] = make_double2(out[0], out[1]);

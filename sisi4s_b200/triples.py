@@ -56,11 +56,14 @@ class TriplesEngine:
     """One GPU's (T) engine: owns a ``pt_handle_t``."""
 
     def __init__(self, o: int, v: int, device: int = 0, engine: int = _lib.PT_ENGINE_FUSED,
-                 keep_raw: bool = False, grid: int = 0, slab_slots: int = 0):
+                 keep_raw: bool = False, grid: int = 0, slab_slots: int = 0, o_all: int | None = None):
+        """``o_all`` > ``o``: engine for a hole subset of a larger problem (pt_create_ex): ``o`` active
+        holes (those of the triples that are run), ``o_all`` holes in the hole contraction."""
         self.lib = _lib.load()
         self.o, self.v = int(o), int(v)
+        self.o_all = self.o if o_all is None else int(o_all)
         self._h = C.c_void_p()
-        _lib.check(self.lib.pt_create(C.byref(self._h), self.o, self.v, int(device)))
+        _lib.check(self.lib.pt_create_ex(C.byref(self._h), self.o, self.o_all, self.v, int(device)))
         self.set_option("keep_raw", int(keep_raw))
         self.set_option("engine", int(engine))
         if grid:
@@ -111,6 +114,12 @@ class TriplesEngine:
         self._shape(t2, (self.v, self.v, self.o, self.o), "CcsdDoublesAmplitudes")
         _lib.check(self.lib.pt_set_doubles(self._h, _ptr(t2)))
 
+    def set_doubles_hole(self, t2_xl):
+        """Hole-term doubles T2[a,b,x,l], x active / l all holes (pt_create_ex engines only)."""
+        t2_xl = _f64(t2_xl)
+        self._shape(t2_xl, (self.v, self.v, self.o, self.o_all), "CcsdDoublesAmplitudes (hole term)")
+        _lib.check(self.lib.pt_set_doubles_hole(self._h, _ptr(t2_xl)))
+
     def set_pphh(self, vabij):
         vabij = _f64(vabij)
         self._shape(vabij, (self.v, self.v, self.o, self.o), "PPHHCoulombIntegrals")
@@ -118,7 +127,7 @@ class TriplesEngine:
 
     def set_hhhp(self, vijka):
         vijka = _f64(vijka)
-        self._shape(vijka, (self.o, self.o, self.o, self.v), "HHHPCoulombIntegrals")
+        self._shape(vijka, (self.o, self.o, self.o_all, self.v), "HHHPCoulombIntegrals")
         _lib.check(self.lib.pt_set_hhhp(self._h, _ptr(vijka)))
 
     def set_ppph(self, vabci, slabs_per_call: int = 0):
@@ -176,6 +185,16 @@ class TriplesEngine:
         per = np.zeros(max(0, end - begin), dtype=np.float64)
         e = C.c_double(0.0)
         _lib.check(self.lib.pt_run(self._h, begin, end, C.byref(e), _ptr(per) if per.size else None))
+        st = self.stats()
+        return RunResult(float(e.value), per, st.seconds_run, st.seconds_kernel, st.flops_algorithmic)
+
+    def run_list(self, triples) -> RunResult:
+        """E_t of an explicit list of sorted-triple indices (enumeration over the active holes)."""
+        idx = np.ascontiguousarray(triples, dtype=np.int64)
+        per = np.zeros(idx.size, dtype=np.float64)
+        e = C.c_double(0.0)
+        _lib.check(self.lib.pt_run_list(self._h, idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(e),
+                                        _ptr(per) if per.size else None))
         st = self.stats()
         return RunResult(float(e.value), per, st.seconds_run, st.seconds_kernel, st.flops_algorithmic)
 
