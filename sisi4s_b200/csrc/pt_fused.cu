@@ -6,17 +6,20 @@
 //      each step contracts up to two 16-row T2 panels with ONE shared 256-pair
 //      tile of a PPPH slab (K = v) plus the hole term (K = o) on FP64 tensor
 //      cores (mma.sync m8n8k4.f64 -> SASS DMMA.8x8x4), operands streamed from the
-//      pre-tiled HBM layouts by cp.async.bulk (TMA engine, SASS UBLKCP) through a
-//      16-stage mbarrier ring filled by a dedicated producer warp;
+//      pre-tiled HBM layouts by cp.async.bulk (TMA engine, SASS UBLKCP) through an
+//      8-stage mbarrier ring of 18 KB stages (K = 8) filled by four producer warps; the
+//      consumers interleave the fragment loads and barrier traffic of the next K-chunk
+//      between the DMMAs of the current one;
 //   2. adds each 16^3 W tile, index-permuted, into the orbit's six X tiles, which
 //      live in TENSOR MEMORY (6 x 32 KB of the SM's 256 KB TMEM, tcgen05.ld/st ->
 //      SASS LDTM/STTM) for the whole item, so that shared memory belongs to the
 //      operand ring -- the v^3 triples blocks are never written to HBM.  The index
 //      permutation goes through a per-group 32 KB staging tile in shared memory;
 //   3. epilogue: the X tiles are copied from TMEM into the (drained) ring region, then
-//      permutational symmetrisation (six index permutations with the spin factors),
-//      singles term, eigenvalue denominator, warp-shuffle reduction, one atomicAdd per
-//      item into the triple's energy.
+//      permutational symmetrisation (generic orbits: a whole S3 point orbit per thread, six
+//      reads, the S3 group table and ONE reciprocal for six points; degenerate orbits: six
+//      permuted reads per point), singles term, eigenvalue denominator, warp-shuffle
+//      reduction, one atomicAdd per item into the triple's energy.
 //
 // This replaces, per sorted triple, getDoublesContribution / the permutation
 // accumulate / divide / spin-factor symmetrise / energy dot of the reference
