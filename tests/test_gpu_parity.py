@@ -130,6 +130,25 @@ def test_ueg_known_answer_of_the_reference():
         assert abs(res.energy - ref_t) <= ABS_TOL, (res.energy, ref_t)
 
 
+def test_ueg_example_plan_from_the_command_line(tmp_path):
+    """examples/ueg_rs1_7occ_26virt: files in the reference's formats under the reference's file
+    names, the plan run as `python -m sisi4s_b200 in.yaml`; result = recorded CCSD + (T) energies."""
+    import subprocess
+    import sys
+    from sisi4s_b200 import tensor_io as TIO
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ex = os.path.join(root, "examples", "ueg_rs1_7occ_26virt")
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    subprocess.run([sys.executable, os.path.join(ex, "make_inputs.py")], cwd=tmp_path, env=env, check=True)
+    out = subprocess.run([sys.executable, "-m", "sisi4s_b200", "in.yaml"], cwd=tmp_path, env=env, check=True,
+                         capture_output=True, text=True).stdout
+    assert "triples=" in out
+    _, e = TIO.read_text(str(tmp_path / "CcsdPerturbativeTriplesEnergy.dat"))
+    assert abs(float(e.reshape(-1)[0]) - (-0.39269658954585018 - 0.0063019625641725016)) <= 1e-8   # CCSD converged to 1e-8
+    e_t = float(out.split("triples=")[1].split()[0])
+    assert abs(e_t - (-0.0063019625641725016)) <= ABS_TOL
+
+
 # ----------------------------------------------------------- structural properties
 def test_partition_invariance_and_ranges():
     inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
