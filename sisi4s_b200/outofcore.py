@@ -59,34 +59,59 @@ def deal(groups, world: int, rank: int):
     return mine
 
 
+def _slices(group, epsi, epsa, T1, T2, Vpphh, Vhhhp, Vppph, vertex, v):
+    """Host side of one group: the sub-tensors its engine needs (contiguous column-major copies)."""
+    holes, trip, _ = group
+    U = np.array(holes)
+    f = np.asfortranarray
+    d = dict(epsi=np.asarray(epsi)[U], T1=f(np.asarray(T1)[:, U]), T2aa=f(np.asarray(T2)[:, :, U][:, :, :, U]),
+             T2al=f(np.asarray(T2)[:, :, U, :]), Vpphh=f(np.asarray(Vpphh)[:, :, U][:, :, :, U]),
+             Vhhhp=f(np.asarray(Vhhhp)[U][:, U]))
+    if Vppph is not None:
+        d["Vppph"] = f(np.asarray(Vppph)[:, :, :, U])
+    else:
+        np_ = vertex.shape[1]
+        sel = np.concatenate([U, np.arange(np_ - v, np_)])
+        d["vertex"] = np.asarray(vertex)[:, sel][:, :, sel]
+    local = {h: n for n, h in enumerate(holes)}
+    lidx = {t: n for n, t in enumerate(_sorted_triples(len(holes)))}
+    d["want"] = [lidx[tuple(local[h] for h in t)] for _, t in trip]
+    return d
+
+
 def run_out_of_core(epsi, epsa, T1, T2, Vpphh, Vhhhp, Vppph=None, vertex=None, block: int = 8,
-                    device: int = 0, world: int = 1, rank: int = 0):
-    """Returns (sum of E_t over this rank's groups, per-triple array with this rank's entries)."""
+                    device: int = 0, world: int = 1, rank: int = 0, prefetch: bool = True):
+    """Returns (sum of E_t over this rank's groups, per-triple array with this rank's entries).
+    With ``prefetch`` the host slicing of the next group runs in a worker thread while the GPU works
+    on the current one (the C ABI calls release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
     o, v = int(len(epsi)), int(len(epsa))
     if Vppph is None and vertex is None:
         raise ValueError("Missing argument: PPPHCoulombIntegrals (or CoulombVertex)")
     per = np.zeros(o * (o + 1) * (o + 2) // 6)
     total = 0.0
-    for holes, trip, _ in deal(block_groups(o, block), world, rank):
-        U = np.array(holes)
-        local = {h: n for n, h in enumerate(holes)}
-        lidx = {t: n for n, t in enumerate(_sorted_triples(len(holes)))}
-        with TriplesEngine(len(holes), v, device=device, o_all=o) as eng:
-            eng.set_eigenenergies(np.asarray(epsi)[U], epsa)
-            eng.set_singles(np.asarray(T1)[:, U])
-            eng.set_doubles(np.asarray(T2)[:, :, U][:, :, :, U])
-            eng.set_doubles_hole(np.asarray(T2)[:, :, U, :])
-            eng.set_pphh(np.asarray(Vpphh)[:, :, U][:, :, :, U])
-            eng.set_hhhp(np.asarray(Vhhhp)[U][:, U])
-            if Vppph is not None:
-                eng.set_ppph(np.asarray(Vppph)[:, :, :, U])
-            else:
-                np_ = vertex.shape[1]
-                sel = np.concatenate([U, np.arange(np_ - v, np_)])
-                eng.set_vertex(np.asarray(vertex)[:, sel][:, :, sel])
-            want = [lidx[tuple(local[h] for h in t)] for _, t in trip]
-            res = eng.run_list(want)
-        for (g, _), e in zip(trip, res.per_triple):
-            per[g] = e
-        total += res.energy
+    mine = deal(block_groups(o, block), world, rank)
+    args = (epsi, epsa, T1, T2, Vpphh, Vhhhp, Vppph, vertex, v)
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        nxt = pool.submit(_slices, mine[0], *args) if mine else None
+        for n, (holes, trip, _) in enumerate(mine):
+            d = nxt.result()
+            nxt = pool.submit(_slices, mine[n + 1], *args) if (prefetch and n + 1 < len(mine)) else None
+            with TriplesEngine(len(holes), v, device=device, o_all=o) as eng:
+                eng.set_eigenenergies(d["epsi"], epsa)
+                eng.set_singles(d["T1"])
+                eng.set_doubles(d["T2aa"])
+                eng.set_doubles_hole(d["T2al"])
+                eng.set_pphh(d["Vpphh"])
+                eng.set_hhhp(d["Vhhhp"])
+                if "Vppph" in d:
+                    eng.set_ppph(d["Vppph"])
+                else:
+                    eng.set_vertex(d["vertex"])
+                res = eng.run_list(d["want"])
+            if nxt is None and n + 1 < len(mine):
+                nxt = pool.submit(_slices, mine[n + 1], *args)
+            for (g, _), e in zip(trip, res.per_triple):
+                per[g] = e
+            total += res.energy
     return total, per
