@@ -6,7 +6,7 @@ integral blocks, as TENS binaries a `TensorWriter mode: binary` step of sisi4s p
 
     python examples/ueg_rs1_7occ_26virt/make_inputs.py && python -m sisi4s_b200 in.yaml
 
-The Hamiltonian comes from oracle/ueg.py (restating UegVertexGenerator.cxx), the amplitudes from the
+The Hamiltonian comes from sisi4s_b200/ueg.py (restating UegVertexGenerator.cxx), the amplitudes from the
 committed fixture tests/golden/ueg_rs1_no7_nv26.npz (oracle/ccsd.py).  Expected output:
 CcsdPerturbativeTriplesEnergy = E(CCSD) + E(T) = -0.39269658979 - 0.00630196257, the values recorded in
 the reference's cc4s.correct.out.yaml:153,169.
@@ -20,8 +20,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from oracle import ueg  # noqa: E402
 from sisi4s_b200 import synthetic as S  # noqa: E402
+from sisi4s_b200 import ueg  # noqa: E402
 from sisi4s_b200 import tensor_io as TIO  # noqa: E402
 
 no, nv = 7, 26

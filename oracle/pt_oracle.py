@@ -27,7 +27,7 @@ this path, but integration-tests/tests/cc4s/ueg/rs1.0-7occ-26virt/
 cc4s.correct.out.yaml:124-169 records MP2, CCSD and (T) energies of the
 uniform electron gas (rs = 1, 7 occupied / 26 virtual states), a system defined
 by closed formulas.  tests/test_known_answers.py regenerates its inputs
-(oracle/ueg.py, restating UegVertexGenerator.cxx; MP2 agrees to 1e-15),
+(sisi4s_b200/ueg.py, restating UegVertexGenerator.cxx; MP2 agrees to 1e-15),
 converges the CCSD amplitudes (oracle/ccsd.py; CCSD energy agrees to 2e-10,
 the reference converged to 1e-8) and checks forms A and B and the C port
 against the recorded (T) = -0.0063019625641725016: agreement 3e-12.

@@ -8,6 +8,7 @@ readers/writers and the triples step:
     - name: TensorReader              {in: {file: T2.bin, mode: binary}, out: {Data: $CcsdDoublesAmplitudes}}
     - name: CcsdPerturbativeTriples   {in: {...}, out: {CcsdPerturbativeTriplesEnergy: $E}}
     - name: TensorWriter              {in: {Data: $E}}
+    (also: UegVertexGenerator {in: {No, Nv, rs}, out: {CoulombVertex, HoleEigenEnergies, ParticleEigenEnergies}})
 
     python -m sisi4s_b200 in.yaml        (cwd-relative file names, like the reference)
 
@@ -100,6 +101,29 @@ class DefineHolesAndParticles(Algorithm):
         holes, particles = TIO.read_eigenenergies(_text(self, "fileName"))
         self.data[_data_name(self, "HoleEigenEnergies")] = holes
         self.data[_data_name(self, "ParticleEigenEnergies")] = particles
+
+
+@register
+class UegVertexGenerator(Algorithm):
+    """Counterpart of reference src/algorithms/UegVertexGenerator.cxx:51-229 (arguments No, Nv, rs;
+    outputs CoulombVertex, HoleEigenEnergies, ParticleEigenEnergies).  The vertex is written in real
+    standing-wave orbitals (sisi4s_b200/ueg.py), for which the reference's real-integral formulas
+    are exact; the reference's own generator writes plane waves "just for profiling" (:148-149).
+    NF and halfGrid are accepted and ignored (the full momentum-transfer grid is always used)."""
+    name = "UegVertexGenerator"
+
+    def run(self):
+        from . import ueg
+        no, nv = self.getIntegerArgument("No"), self.getIntegerArgument("Nv")
+        rs = self.getRealArgument("rs")
+        if no <= 0:
+            raise SisiException("No larger zero please")          # :63
+        if rs <= 0.0:
+            raise SisiException("Invalid rs")                     # :64
+        epsi, epsa, gamma = ueg.make_ueg(no, nv, rs)
+        self.data[_data_name(self, "CoulombVertex")] = gamma
+        self.data[_data_name(self, "HoleEigenEnergies")] = epsi
+        self.data[_data_name(self, "ParticleEigenEnergies")] = epsa
 
 
 def parse_plan(text: str) -> list[dict]:

@@ -1,4 +1,6 @@
-"""Uniform-electron-gas inputs for the (T) step -- TEST INFRASTRUCTURE (oracle side).
+"""Uniform-electron-gas inputs for the (T) step: host-side input generator (like synthetic.py),
+the counterpart of the reference's UegVertexGenerator algorithm (registered under that name in
+plan.py).  No part of the (T) computation happens here.
 
 Restates the model the reference generates in UegVertexGenerator::run (reference
 src/algorithms/UegVertexGenerator.cxx:51-229; Madelung constant :10-30, exchange :37-41, plane-wave

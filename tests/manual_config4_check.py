@@ -4,7 +4,7 @@ input set (87 GB) resident.  The PPPH integrals are built on the device from the
 triples are checked against the CPU oracle (oracle/pt_oracle.c), which reads only the three PPPH
 slabs of a triple from a sparse memory-mapped [v,v,v,o] file.
 
-    python scripts/config4_check.py [o v npart part]     -> gpurun_out/config4_check.json
+    python tests/manual_config4_check.py [o v npart part]     -> gpurun_out/config4_check.json
 """
 import json, os, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

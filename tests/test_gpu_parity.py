@@ -115,10 +115,10 @@ def test_ueg_known_answer_of_the_reference():
     """UEG rs=1.0, 7 occupied / 26 virtual: the CUDA path against the (T) correlation energy the
     reference records for this system, -0.0063019625641725016
     (integration-tests/tests/cc4s/ueg/rs1.0-7occ-26virt/cc4s.correct.out.yaml:166-169), on inputs
-    restated from the reference's formulas (oracle/ueg.py) and converged CCSD amplitudes
+    restated from the reference's formulas (sisi4s_b200/ueg.py) and converged CCSD amplitudes
     (tests/golden/ueg_rs1_no7_nv26.npz; see tests/test_known_answers.py).  Both reference
     contracts: PPPH integrals and Coulomb vertex."""
-    from oracle import ueg
+    from sisi4s_b200 import ueg
     ref_t = -0.0063019625641725016
     epsi, epsa, gamma = ueg.make_ueg(7, 26, 1.0)
     vpphh, vhhhp, vppph = S.integrals_from_vertex(gamma, 7, 26)

@@ -9,7 +9,7 @@ energies of the pipeline  vertex -> integrals -> CCSD -> perturbative triples:
     (T) correlation     -0.0063019625641725016   (:169)
 
 Its input files are not in the repository (downloaded test resources), but the system is defined by
-closed formulas, restated in oracle/ueg.py from the reference's UegVertexGenerator.  These tests pin
+closed formulas, restated in sisi4s_b200/ueg.py from the reference's UegVertexGenerator.  These tests pin
 (i) that restatement (MP2 to 1e-13), (ii) the amplitude solver that produced the stored CCSD
 amplitudes (CCSD energy to 1e-8, the reference's convergence threshold) and (iii) the (T)
 restatements -- NumPy loop form, full-tensor form, C port -- on those amplitudes, to 1e-9 Eh (the
@@ -21,7 +21,8 @@ import os
 import numpy as np
 import pytest
 
-from oracle import ccsd, ueg
+from oracle import ccsd
+from sisi4s_b200 import ueg
 from oracle import pt_oracle as O
 from sisi4s_b200 import synthetic as S
 

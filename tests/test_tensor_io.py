@@ -110,3 +110,18 @@ def test_plan_parsing_and_file_algorithms(tmp_path, monkeypatch):
         open("bad.yaml", "w").write("- name: HartreeFockFromGaussian\n  in: {}\n")
         run_plan_file("bad.yaml", log=lambda *_: None)
     assert [n["name"] for n in parse_plan(open("in.yaml").read())] == ["TensorReader", "TensorWriter", "TensorReader"]
+
+
+def test_ueg_vertex_generator_step():
+    """UegVertexGenerator as a plan step: closed-shell checks and outputs of the reference algorithm."""
+    from sisi4s_b200.triples import AlgorithmFactory
+    data = {}
+    args = dict(No=7, Nv=26, rs=1.0, CoulombVertex="$CoulombVertex", HoleEigenEnergies="$HoleEigenEnergies",
+                ParticleEigenEnergies="$ParticleEigenEnergies")
+    AlgorithmFactory.create("UegVertexGenerator", args, data).run()
+    assert data["CoulombVertex"].shape == (257, 33, 33) and data["HoleEigenEnergies"].shape == (7,)
+    assert data["HoleEigenEnergies"].max() < data["ParticleEigenEnergies"].min()
+    with pytest.raises(ValueError, match="closed shells"):
+        AlgorithmFactory.create("UegVertexGenerator", dict(args, No=5), data).run()
+    with pytest.raises(SisiException, match="Invalid rs"):
+        AlgorithmFactory.create("UegVertexGenerator", dict(args, rs=0.0), data).run()
