@@ -353,7 +353,7 @@ def main():
     if rank == 0:
         traffic = None
         prof = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
-        if os.path.exists(prof):
+        if os.path.exists(prof) and args.workload == "o40v300":   # the capture is of this workload's step
             try:
                 # measured on one N=1 step (profiles/r01d_step_traffic.csv); a rank's launch covers 1/world of it
                 traffic = json.load(open(prof)).get("dram_bytes_per_launch") / world
