@@ -126,11 +126,123 @@ class UegVertexGenerator(Algorithm):
         self.data[_data_name(self, "ParticleEigenEnergies")] = epsa
 
 
+@register
+class CoulombIntegralsFromVertex(Algorithm):
+    """Real Coulomb integral blocks from the vertex, reference src/algorithms/
+    CoulombIntegralsFromVertex.cxx:390-433 (directly computed blocks, V = Re.Re + Im.Im with the
+    reference's index strings) and :436-560 (blocks derived by index permutation).  Host-side
+    (NumPy); `complex: 1` and `antisymmetrize: 1` are not supported.  Only the blocks named in the
+    step's `out:` map are built."""
+    name = "CoulombIntegralsFromVertex"
+    # name -> (first vertex part, its indices, second part, its indices, output indices)
+    DIRECT = {"PPHHCoulombIntegrals": ("ai", "ai", "ai", "bj", "abij"),      # :402-403
+              "HHHHCoulombIntegrals": ("ij", "ik", "ij", "jl", "ijkl"),      # :409-410
+              "HHHPCoulombIntegrals": ("ij", "ik", "ai", "aj", "ijka"),      # :416-417
+              "PPPPCoulombIntegrals": ("ab", "ac", "ab", "bd", "abcd"),      # :423-424
+              "PPPHCoulombIntegrals": ("ab", "ac", "ai", "bi", "abci"),      # :430-431
+              "PHPHCoulombIntegrals": ("ab", "ab", "ij", "ij", "aibj")}      # :395-396
+    # name -> (source block, source index string, output index string)
+    DERIVED = {"HPPHCoulombIntegrals": ("PPHHCoulombIntegrals", "baij", "iabj"),   # :443
+               "HPHPCoulombIntegrals": ("PHPHCoulombIntegrals", "aibj", "iajb"),   # :455
+               "HPPPCoulombIntegrals": ("PPPHCoulombIntegrals", "cbai", "iabc"),   # :467
+               "HHPHCoulombIntegrals": ("HHHPCoulombIntegrals", "jika", "ijak"),   # :479
+               "HHPPCoulombIntegrals": ("PPHHCoulombIntegrals", "abij", "ijab"),   # :491
+               "PPHPCoulombIntegrals": ("PPPHCoulombIntegrals", "baci", "abic"),   # :503
+               "PHHPCoulombIntegrals": ("PPHHCoulombIntegrals", "abji", "aijb"),   # :515
+               "PHPPCoulombIntegrals": ("PPPHCoulombIntegrals", "bcai", "aibc"),   # :527
+               "PHHHCoulombIntegrals": ("HHHPCoulombIntegrals", "kjia", "aijk"),   # :539
+               "HPHHCoulombIntegrals": ("HHHPCoulombIntegrals", "jkia", "iajk")}   # :551
+
+    def _direct(self, name, parts):
+        p1, i1, p2, i2, out = self.DIRECT[name]
+        a, b = parts[p1], parts[p2]
+        return np.asfortranarray(np.einsum(f"G{i1},G{i2}->{out}", a.real, b.real, optimize=True)
+                                 + np.einsum(f"G{i1},G{i2}->{out}", a.imag, b.imag, optimize=True))
+
+    def run(self):
+        if self.getIntegerArgument("complex", 0) or self.getIntegerArgument("antisymmetrize", 0):
+            raise SisiException("CoulombIntegralsFromVertex: only real, non-antisymmetrized integrals")
+        g = self.getTensorArgument("CoulombVertex")
+        no = int(self.getTensorArgument("HoleEigenEnergies").shape[0])
+        nv = int(self.getTensorArgument("ParticleEigenEnergies").shape[0])
+        np_ = g.shape[1]
+        h, pt = slice(0, no), slice(np_ - nv, np_)                       # particles = last Nv states (:121-136)
+        parts = {"ij": g[:, h, h], "ai": g[:, pt, h], "ab": g[:, pt, pt]}
+        cache = {}
+        for name in list(self.DIRECT) + list(self.DERIVED):
+            if not self.isArgumentGiven(name):
+                continue
+            if name in self.DIRECT:
+                cache.setdefault(name, self._direct(name, parts))
+                val = cache[name]
+            else:
+                src, si, so = self.DERIVED[name]
+                cache.setdefault(src, self._direct(src, parts))
+                val = np.asfortranarray(np.einsum(f"{si}->{so}", cache[src]))
+            self.data[_data_name(self, name)] = val
+
+
+@register
+class CcsdEnergyFromCoulombIntegralsReference(Algorithm):
+    """CCSD step in front of the triples (reference CcsdEnergyFromCoulombIntegralsReference.cxx /
+    ClusterSinglesDoublesAlgorithm.cxx:37-128; outputs CcsdEnergy, CcsdSinglesAmplitudes,
+    CcsdDoublesAmplitudes).  Solved by sisi4s_b200/ccsd.py from the CoulombVertex (library GEMMs on the
+    GPU), so the step needs `CoulombVertex` in its `in:` map; the integral-block arguments of the
+    reference's plans are accepted and ignored.  Runs on `device` (default cuda:0; `device: cpu` must be
+    asked for explicitly)."""
+    name = "CcsdEnergyFromCoulombIntegralsReference"
+
+    def run(self):
+        import torch
+        from . import ccsd
+        if not self.isArgumentGiven("CoulombVertex"):
+            raise SisiException("Missing argument: CoulombVertex")
+        device = _text(self, "device", "cuda:0")
+        if device.startswith("cuda") and not torch.cuda.is_available():
+            raise SisiException("CcsdEnergyFromCoulombIntegralsReference: no CUDA device (pass `device: cpu` to run on the host)")
+        out = []
+        res = ccsd.solve_ccsd(self.getTensorArgument("HoleEigenEnergies"), self.getTensorArgument("ParticleEigenEnergies"),
+                              self.getTensorArgument("CoulombVertex"), device,
+                              energy_convergence=self.getRealArgument("energyConvergence", 1e-6),
+                              amplitudes_convergence=self.getRealArgument("amplitudesConvergence", 1e-5),
+                              max_iterations=self.getIntegerArgument("maxIterations", 16),
+                              max_residua=self.getIntegerArgument("maxResidua", 4), log=out.append)
+        self.log = {"e": res["energy"]}
+        self.iterations = out
+        if not res["converged"]:
+            raise SisiException(f"CCSD did not converge in {res['iterations']} iterations")
+        self.setRealArgument("CcsdEnergy", res["energy"])
+        for key, val in (("CcsdSinglesAmplitudes", res["T1"]), ("CcsdDoublesAmplitudes", res["T2"])):
+            if self.isArgumentGiven(key):
+                self.data[_data_name(self, key)] = val
+
+
+@register
+class CcsdEnergyFromCoulombIntegrals(CcsdEnergyFromCoulombIntegralsReference):
+    """Same step under the reference's other name (takes the CoulombVertex in the reference, too)."""
+    name = "CcsdEnergyFromCoulombIntegrals"
+
+
+def _load_yaml12(text: str):
+    """yaml-cpp (the reference's parser) follows YAML 1.2: only true/false are booleans.  PyYAML's
+    YAML 1.1 resolver would turn the argument key `No` of UegVertexGenerator into False."""
+    import re
+    import yaml
+
+    class Loader(yaml.SafeLoader):
+        pass
+
+    Loader.yaml_implicit_resolvers = {k: [(tag, rx) for tag, rx in v if tag != "tag:yaml.org,2002:bool"]
+                                      for k, v in yaml.SafeLoader.yaml_implicit_resolvers.items()}
+    Loader.add_implicit_resolver("tag:yaml.org,2002:bool", re.compile(r"^(?:true|True|TRUE|false|False|FALSE)$"),
+                                 list("tTfF"))
+    return yaml.load(text, Loader=Loader)
+
+
 def parse_plan(text: str) -> list[dict]:
     """Parser::parse (reference src/Parser.cxx:22-109): a YAML sequence of
     {name, in: {..}, out: {..}} nodes; other keys of a node (anchors on a Nop step) are ignored."""
-    import yaml
-    nodes = yaml.safe_load(text)
+    nodes = _load_yaml12(text)
     if not isinstance(nodes, list):
         raise SisiException("the execution plan must be a YAML sequence of algorithms")
     plan = []

@@ -149,6 +149,17 @@ def test_ueg_example_plan_from_the_command_line(tmp_path):
     assert abs(e_t - (-0.0063019625641725016)) <= ABS_TOL
 
 
+def test_ueg_pipeline_plan_on_the_device():
+    """examples/ueg_rs1_7occ_26virt/pipeline.yaml: generator -> integrals -> CCSD (device) -> (T) (device);
+    both recorded energies of the reference's test at once."""
+    from sisi4s_b200.plan import run_plan_file
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = run_plan_file(os.path.join(root, "examples", "ueg_rs1_7occ_26virt", "pipeline.yaml"), log=lambda *_: None)
+    assert abs(data["CcsdEnergy"] - (-0.39269658954585018)) <= 1e-8
+    e_t = data["PerturbativeTriplesEnergy"] - data["CcsdEnergy"]
+    assert abs(e_t - (-0.0063019625641725016)) <= ABS_TOL, e_t
+
+
 # ----------------------------------------------------------- structural properties
 def test_partition_invariance_and_ranges():
     inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
