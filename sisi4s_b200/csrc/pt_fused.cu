@@ -138,8 +138,13 @@ __device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 constexpr int TMEM_COLS = 512;
 // register split (setmaxnreg): 384 threads x 168 at launch = 8 x 32 x 224 + 4 x 32 x 56
-constexpr int CONSUMER_REGS = 224;
-constexpr int PRODUCER_REGS = 56;
+#ifndef PT_CONSUMER_REGS
+#define PT_CONSUMER_REGS 224
+#define PT_PRODUCER_REGS 56
+#endif
+constexpr int CONSUMER_REGS = PT_CONSUMER_REGS;
+constexpr int PRODUCER_REGS = PT_PRODUCER_REGS;
+static_assert(NCONSUMER_WARPS * 32 * CONSUMER_REGS + NPRODUCER_WARPS * 32 * PRODUCER_REGS <= 65536, "register file");
 constexpr int TMEM_COLS_PER_TILE = 64;
 
 __device__ __forceinline__ int sel3(int a, int b, int c, int idx) {
