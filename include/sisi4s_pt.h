@@ -61,6 +61,7 @@ typedef struct PtStats {
   int32_t sm_count;
   int32_t reserved;
   int64_t slab_loads;        /* PPPH slabs (re)built or re-uploaded on demand (slab_slots < o) */
+  int64_t groups_staged;     /* hole-block groups whose T2 / PPHH / HHHP blocks were staged (hole_block)  */
 } PtStats;
 
 /* ---- lifecycle ---------------------------------------------------------- */
@@ -90,8 +91,38 @@ const char *pt_version(void);
  * tensor exceeds HBM (BASELINE configs[4]); pt_run then walks the sorted
  * triples by hole blocks of width S/3 and (re)builds slabs on demand from the
  * resident vertex or re-uploads them from the pt_set_ppph_host tensor; 0 = all
- * resident; set BEFORE the PPPH integrals / vertex).                          */
+ * resident; set BEFORE the PPPH integrals / vertex);
+ * "hole_block" (b: hole-blocked OUT-OF-CORE mode for shapes whose hole-indexed
+ * tensors exceed one GPU -- BASELINE configs[4], o=100 v=800: T2, its second
+ * packing and PPHH are 51 GB each, PPPH 410 GB.  Set FIRST, on a pt_create
+ * handle.  The setters then take the FULL tensors of the problem but keep only
+ * what fits: pt_set_doubles / pt_set_pphh / pt_set_ppph_host record the
+ * caller-owned host pointers (they must stay valid until pt_destroy),
+ * pt_set_hhhp uploads the o^3 v tensor once, pt_set_vertex keeps the vertex
+ * image resident.  pt_run / pt_run_list walk their triples by hole-block
+ * triples (I<=J<=K) of width b: before each group's launch the T2 / PPHH /
+ * HHHP blocks of its <= 3b active holes are staged into device buffers that
+ * were allocated once for 3b holes, and the group's PPPH slabs are made
+ * resident (rebuilt from the vertex, like the reference does per triple,
+ * CcsdPerturbativeTriples.cxx:89-92, or uploaded from the host tensor; LRU
+ * over slab_slots >= 3b slots, K fastest so consecutive groups share the slabs
+ * of blocks I and J).  E_t of a triple is bitwise the number the all-resident
+ * run gives.  pt_partition ranges work unchanged: a contiguous range of the
+ * (i,j,k) enumeration touches few I blocks);
+ * "async_upload" (1: the pt_set_* calls only enqueue their copies and packing
+ * kernels on the handle's stream and return; the host buffers must then stay
+ * valid and unmodified until pt_sync or pt_run returns.  0 (default): every
+ * setter returns after its copy has completed);
+ * "pin_host" (1: page-lock the caller's large tensors in hole_block mode so
+ * the per-group block copies run at full DMA speed).                          */
 int pt_set_option(pt_handle_t h, const char *key, int64_t value);
+/* waits for everything the setters enqueued (async_upload) and reports their errors */
+int pt_sync(pt_handle_t h);
+/* Device memory (bytes) a handle for (o, v) will hold with the given slab_slots / hole_block
+ * options (0 = unset), PPPH given as a tensor; host-only, no GPU needed.  This is the number the
+ * plugin's dryRun reports in place of the reference's CTF estimate
+ * (CcsdPerturbativeTriples.cxx:250-284).                                      */
+int64_t pt_estimate_device_bytes(int o, int v, int slab_slots, int hole_block);
 
 /* ---- inputs (names = the reference's YAML argument keys) ------------------ */
 /* HoleEigenEnergies[o], ParticleEigenEnergies[v]
@@ -126,6 +157,18 @@ int pt_set_ppph_host(pt_handle_t h, const double *vabci);
  * With slab_slots < o the vertex stays resident on the device and slabs are
  * rebuilt when needed, like the reference does per triple (:89-92).           */
 int pt_set_vertex(pt_handle_t h, int nf, int np, const double *gamma_re, const double *gamma_im);
+/* After pt_set_vertex: build PPHHCoulombIntegrals (Vabij["abij"] = G["Gai"] G["Gbj"],
+ * CoulombIntegralsFromVertex.cxx:402-403) and HHHPCoulombIntegrals (Vijka["ijka"] = G["Gik"] G["Gaj"],
+ * :416-417) on the device from the resident vertex and use them as the step's inputs, so the
+ * CoulombVertex contract needs neither tensor from the host (in hole_block mode PPHH is rebuilt
+ * per group).  Replaces pt_set_pphh + pt_set_hhhp.                              */
+int pt_use_vertex_integrals(pt_handle_t h);
+/* CoulombIntegralsFromVertex on the device: after pt_set_vertex, computes one
+ * real integral block from the resident vertex with the FP64 tensor-core GEMM and copies it to
+ * `out` (caller-owned host memory, column-major):
+ *   "PPHH" [v,v,o,o] (:402-403), "HHHP" [o,o,o,v] (:416-417), "PPPH" [v,v,v,o] (:430-431, one hole
+ *   slab at a time).  Not available on hole-subset engines (pt_create_ex).        */
+int pt_vertex_integrals(pt_handle_t h, const char *block, double *out);
 
 /* ---- run ------------------------------------------------------------------ */
 /* number of sorted hole triples i<=j<=k = o(o+1)(o+2)/6, enumerated in the
@@ -151,6 +194,10 @@ int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, 
 /* FP64 issue-rate microbenchmarks on the handle's device: mode 0 = DMMA.8x8x4,
  * mode 1 = DFMA.  Returns achieved TFLOP/s over `iters` inner iterations.     */
 int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double *tflops, double *sm_mhz_est);
+/* kernel-only timing of the integrals-from-vertex GEMM on the resident vertex: what = 0 one packed
+ * PPPH hole slab (2 * 2NF * v^3 FLOP), 1 = the PPHH block (2 * 2NF * v^2 o^2 FLOP); average device
+ * seconds per build over `reps` launches (CUDA events) and the algorithmic FLOP of one build.   */
+int pt_bench_vertex_gemm(pt_handle_t h, int what, int reps, double *seconds, double *flop);
 
 #ifdef __cplusplus
 }

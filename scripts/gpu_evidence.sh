@@ -11,5 +11,5 @@ echo "== ncu full"; timeout 900 ncu --set full --clock-control none --import-sou
 python tools/ncu_summary.py gpurun_out/${TAG}_fused.ncu-rep > gpurun_out/${TAG}_fused_summary.txt 2>&1; head -20 gpurun_out/${TAG}_fused_summary.txt
 echo "== launches"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/${TAG}_bench_under_ncu.log 2>&1; tail -2 gpurun_out/${TAG}_bench_under_ncu.log; wc -l gpurun_out/${TAG}_launches.csv
 echo "== dram traffic of one bench step"; timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:pt_fused -c 1 --csv --log-file gpurun_out/${TAG}_step_traffic.csv python scripts/prof_run.py step 3 1 2>&1 | tail -1; tail -4 gpurun_out/${TAG}_step_traffic.csv | cut -d, -f13-
-echo "== feed ceiling"; timeout 600 python scripts/feed_test.py 2>&1 | tail -4 | tee gpurun_out/${TAG}_feed.txt
+echo "== feed ceiling"; timeout 600 python scripts/feed_ceiling.py 2>&1 | tail -4 | tee gpurun_out/${TAG}_feed.txt
 echo "== reference arm"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_reference.json

@@ -1,22 +1,23 @@
-"""Device construction of the PPPH slabs from the Coulomb vertex (pt_set_vertex) at a realistic
-auxiliary dimension: time + one slab checked against numpy through the W-tile debug entry."""
-import json, os, sys, time
+"""Integrals-from-vertex GEMM (pt_pack.cu: vertex_gemm_kernel) at realistic auxiliary dimensions:
+kernel-only device time of one packed PPPH slab and of the PPHH block, as FP64 TFLOP/s.
+
+    python scripts/vertex_timing.py [o v nf ...]   -> gpurun_out/vertex_timing.json
+"""
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 from sisi4s_b200 import synthetic as S
 from sisi4s_b200.triples import TriplesEngine
-o, v, nf = (int(x) for x in (sys.argv[1:4] + ["40", "300", "600"][len(sys.argv) - 1:]))
-G = S.make_vertex(o, v, seed=7, nf=nf)
-inp = S.make_inputs(o, v, seed=7, kind="random") if v <= 64 else None
-with TriplesEngine(o, v) as eng:
-    t0 = time.time()
-    eng.set_vertex(G)
-    st = eng.stats()
-    wall = time.time() - t0
-    flop = 2.0 * 2.0 * nf * v ** 3 * o
-    h2d_s = st.bytes_h2d / 25e9
-    out = {"o": o, "v": v, "nf": nf, "device_s_total": st.seconds_upload, "wall_s": wall, "flop": flop,
-           "tflops_incl_h2d_and_pack": flop / st.seconds_upload * 1e-12, "h2d_gb": st.bytes_h2d / 1e9}
-print(json.dumps(out))
+a = [int(x) for x in sys.argv[1:]] or [40, 300, 600, 40, 300, 24, 24, 512, 1024]
+out = []
+for o, v, nf in zip(a[0::3], a[1::3], a[2::3]):
+    G = S.make_vertex(o, v, seed=7, nf=nf)
+    with TriplesEngine(o, v, slab_slots=3 if o > 3 else 0) as eng:   # 3 slots: only the vertex + 3 slabs live
+        eng.set_vertex(G)
+        rec = {"o": o, "v": v, "nf": nf}
+        for what, name in ((0, "ppph_slab_packed"), (1, "pphh")):
+            s, f = eng.bench_vertex_gemm(what, 3)
+            rec[name] = {"seconds": s, "flop": f, "tflops": f / s * 1e-12, "out_gb_per_s": (v ** 3 if what == 0 else v * v * o * o) * 8 / s * 1e-9}
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/vertex_timing.json", "w"), indent=1)

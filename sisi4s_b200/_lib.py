@@ -30,6 +30,7 @@ class PtStats(C.Structure):
         ("sm_count", C.c_int32),
         ("reserved", C.c_int32),
         ("slab_loads", C.c_int64),
+        ("groups_staged", C.c_int64),
     ]
 
 
@@ -43,6 +44,10 @@ SYMBOLS = {
     "pt_last_error": (C.c_char_p, []),
     "pt_version": (C.c_char_p, []),
     "pt_set_option": (C.c_int, [_H, C.c_char_p, C.c_int64]),
+    "pt_sync": (C.c_int, [_H]),
+    "pt_estimate_device_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pt_use_vertex_integrals": (C.c_int, [_H]),
+    "pt_vertex_integrals": (C.c_int, [_H, C.c_char_p, _DP]),
     "pt_set_eigenenergies": (C.c_int, [_H, _DP, _DP]),
     "pt_set_singles": (C.c_int, [_H, _DP]),
     "pt_set_doubles": (C.c_int, [_H, _DP]),
@@ -59,6 +64,7 @@ SYMBOLS = {
     "pt_get_stats": (C.c_int, [_H, C.POINTER(PtStats)]),
     "pt_debug_w_tile": (C.c_int, [_H] + [C.c_int] * 6 + [_DP]),
     "pt_bench_fp64": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, _DP, _DP]),
+    "pt_bench_vertex_gemm": (C.c_int, [_H, C.c_int, C.c_int, _DP, _DP]),
 }
 
 _lib = None

@@ -96,7 +96,8 @@ struct FusedParams {
   int order;              // 0: triple-major (orbit fastest), 1: orbit-major (triple fastest; L2 reuse of PPPH tiles)
   int debug;              // measurement switches (wrong results): 1 = consumers skip LDS/DMMA (operand-feed ceiling), 4 = skip the scatter, 8 = skip the epilogue point loops
   long long nitems;       // ntriples * norbits
-  double* e_triple;       // [ntriples], accumulated with atomicAdd
+  double* e_item;         // [nitems]: per-item partial sums (one plain store per item; summed per triple in a
+                          // fixed order by reduce_items_kernel, so E_t is bitwise reproducible)
   unsigned int* sync_ctr; // item-round barrier counter (zeroed per launch); nullptr = CTAs run free
   int sync_every;         // barrier before every sync_every-th item round
 };
@@ -121,10 +122,33 @@ struct WTileJob { int x, y, z, P, Q, R; };
 cudaError_t launch_pack_vt_slab(const double* raw_slab, double* vt_slab, Dims d, cudaStream_t s);
 cudaError_t launch_pack_tt(const double* t2, double* tt, Dims d, cudaStream_t s);
 cudaError_t launch_pack_t2h(const double* t2, double* t2h, Dims d, cudaStream_t s);
-cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, cudaStream_t s);
+cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, const int* hmap, cudaStream_t s);
 cudaError_t launch_pphh_symsum(const double* pphh, double* qsum, Dims d, cudaStream_t s);
-cudaError_t launch_ppph_slab_from_vertex(const double* gre, const double* gim, int nf, int np,
-                                         int z, double* raw_slab, Dims d, cudaStream_t s);
+cudaError_t launch_reduce_items(const double* e_item, int ntriples, int norbits, int order, double* e_triple,
+                                cudaStream_t s);
+
+// ---- integrals from the vertex (pt_pack.cu): one K-major image of the vertex, batched DMMA GEMMs
+enum { VG_STRIDED = 0, VG_PACKED = 1 };
+struct VgParams {
+  const double* gp;        // Gp[kc][r][4], r = p + np q
+  long long rows_padded;
+  int kp4;                 // K chunks of 4 (K = 2 nf padded to a multiple of 16)
+  int mode;
+  // VG_STRIDED: batch (b0, b1) -> first rows / output offset; optional index maps (hole subsets)
+  int nb0, nb1;
+  const int *map0, *map1;
+  long long a_base, a_s0, a_s1, b_base, b_s0, b_s1, o_s0, o_s1;
+  int M, N;
+  long long sm, sn;
+  // VG_PACKED: one PPPH hole slab in the Vt layout
+  int np, a0, v, nr, nk4;
+  double* out;
+};
+inline long long vertex_rows_padded(int np) { return (long long)np * np + 256; }
+inline int vertex_kp4(int nf) { return ((2 * nf + 15) / 16) * 4; }
+cudaError_t vertex_gemm_configure();
+cudaError_t launch_pack_vertex(const double* gre, const double* gim, int nf, int np, double* gp, cudaStream_t s);
+cudaError_t launch_vertex_gemm(const VgParams& p, cudaStream_t s);
 
 cudaError_t fused_configure(int* smem_bytes_out);
 cudaError_t launch_fused(const FusedParams& p, int grid, cudaStream_t s);

@@ -19,7 +19,7 @@
 //      permutational symmetrisation (generic orbits: a whole S3 point orbit per thread, six
 //      reads, the S3 group table and ONE reciprocal for six points; degenerate orbits: six
 //      permuted reads per point), singles term, eigenvalue denominator, warp-shuffle
-//      reduction, one atomicAdd per item into the triple's energy.
+//      reduction, one store per item (summed per triple in a fixed order by reduce_items_kernel).
 //
 // This replaces, per sorted triple, getDoublesContribution / the permutation
 // accumulate / divide / spin-factor symmetrise / energy dot of the reference
@@ -150,7 +150,7 @@ constexpr int TMEM_COLS_PER_TILE = 64;
 __device__ __forceinline__ int sel3(int a, int b, int c, int idx) {
   return idx == 0 ? a : (idx == 1 ? b : c);
 }
-// X-tile element index with the XOR swizzle chosen by tools/swizzle_search.py:
+// X-tile element index with the XOR swizzle (found by exhaustive search over XOR-linear maps of the three nibbles):
 // low nibble x0 ^ x1 ^ bitswap13(x2); at most 2-way bank conflicts for every
 // permuted accumulate / read pattern of the kernel.
 __device__ __forceinline__ int xt_index(int x0, int x1, int x2) {
@@ -952,7 +952,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
       double s = 0.0;
 #pragma unroll
       for (int w = 0; w < NCONSUMER_WARPS; ++w) s += red[w];
-      atomicAdd(p.e_triple + t, s);
+      p.e_item[item] = s;   // one plain store per item; per-triple sums are a fixed-order second pass
     }
   }
   consumer_barrier();

@@ -11,6 +11,8 @@
 
 namespace pt {
 
+static inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
 // raw_slab[b + v*(c + v*d)] = Vppph[b,c,d,z]  ->  Vt slab [Q][R][dc][n][kk]
 __global__ void __launch_bounds__(256) pack_vt_slab_kernel(const double* __restrict__ raw,
                                                            double* __restrict__ vt, Dims d) {
@@ -88,9 +90,10 @@ __global__ void __launch_bounds__(256) pack_t2h_kernel(const double* __restrict_
   dst[1] = make_double2(out[2], out[3]);
 }
 
-// Ut[z][y][R][lc][c][kk] = -Vhhhp[y, z, l=4lc+kk, c=16R+c]   (raw [o,o,ol,v])
+// Ut[z][y][R][lc][c][kk] = -Vhhhp[y, z, l=4lc+kk, c=16R+c]   (raw [o,o,ol,v]; with `hmap` the source is
+// the FULL tensor [ol,ol,ol,v] and the active holes y, z are looked up: hole-blocked mode)
 __global__ void __launch_bounds__(256) pack_ut_kernel(const double* __restrict__ hhhp,
-                                                      double* __restrict__ ut, Dims d) {
+                                                      double* __restrict__ ut, Dims d, const int* __restrict__ hmap) {
   const size_t rows = (size_t)d.o * d.o * d.nr * d.nl4 * 16;
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= rows) return;
@@ -101,12 +104,13 @@ __global__ void __launch_bounds__(256) pack_ut_kernel(const double* __restrict__
   const int y = r % d.o;
   const int z = r / d.o;
   const int c = TILE * R + c16;
-  const size_t o = d.o;
+  const size_t o = hmap ? d.ol : d.o;
+  const size_t ys = hmap ? hmap[y] : y, zs = hmap ? hmap[z] : z;
   double out[4];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const int l = 4 * lc + kk;
-    out[kk] = (c < d.v && l < d.ol) ? -hhhp[y + o * (z + o * (l + (size_t)d.ol * c))] : 0.0;
+    out[kk] = (c < d.v && l < d.ol) ? -hhhp[ys + o * (zs + o * (l + (size_t)d.ol * c))] : 0.0;
   }
   double2* dst = reinterpret_cast<double2*>(ut + gid * 4);
   dst[0] = make_double2(out[0], out[1]);
@@ -141,92 +145,235 @@ __global__ void __launch_bounds__(256) pphh_symsum_kernel(const double* __restri
   }
 }
 
-// PPPH slab z from the Coulomb vertex (reference CoulombIntegralsFromVertex.cxx:430-431,
-// Vabci["abci"] = ReG["Gac"] ReG["Gbi"] + ImG["Gac"] ImG["Gbi"], particles = last v states):
-//   slab[a + v*(b + v*c)] = sum_F G[F,a0+a,a0+c] G[F,a0+b,z]   (Re.Re + Im.Im)
-// G is column-major [F + nf*(p + np*q)], i.e. both operands are K-contiguous.  A GEMM with
-// M = (a,c) pairs, N = b, K = 2 NF on the FP64 tensor pipe: 128 x 64 output tile per CTA, K chunks
-// of 16 staged through shared memory (k-major, padded: conflict-free fragment reads), each of the
-// 8 warps owns 32 x 32 of the tile = 4 x 4 DMMA.8x8x4 accumulators.
+// =====================================================================================
+// Coulomb integrals from the vertex on the FP64 tensor pipe (reference
+// src/algorithms/CoulombIntegralsFromVertex.cxx:402-403 (Vabij), :416-417 (Vijka), :430-431
+// (Vabci): V = Re G . Re G + Im G . Im G with the index strings quoted at each launcher).
+//
+// Every block is a (batched) GEMM  C[m,n] = sum_K A[rowA(m)][K] B[rowB(n)][K]  whose operand
+// rows are rows (p,q) of ONE K-major image of the vertex:
+//
+//   Gp[kc][r][kk] = K-element 4 kc + kk of row r = p + Np q,   K = (Re G[0..NF), Im G[0..NF), 0-pad)
+//
+// so Re.Re + Im.Im is a single contraction of length 2 NF, a run of 16 rows x 4 K-values is one
+// contiguous 512-byte bulk copy, and a DMMA fragment load is `base + lane` (conflict-free), the
+// same trick as the (T) kernel's layouts.  pack_vertex_kernel builds the image once per vertex.
+//
+// vertex_gemm_kernel: CTA tile 64 (M) x 128 (N), K stages of 16 through a 4-deep mbarrier ring
+// filled by one producer warp (20 cp.async.bulk copies per stage, one per lane), 8 consumer warps
+// with a 32 x 32 register tile each (4 x 4 DMMA.8x8x4 accumulators), two CTAs per SM so one CTA's
+// prologue/epilogue overlaps the other's main loop.  Output modes:
+//   VG_STRIDED : out[outoff(batch) + m sm + n sn], masked to m < M, n < N
+//   VG_PACKED  : straight into the packed PPPH layout Vt[Q][R][dc][16 b][16 c][4 d] of one hole slab
+//                (M tile = 16 b x 4 d, N tile = 128 c), zero for padded b/c/d -- no raw slab round trip.
+namespace {
+
+__device__ __forceinline__ uint32_t vg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vg_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vg_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void vg_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void vg_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
       : "+d"(c0), "+d"(c1)
       : "d"(a), "d"(b));
 }
 
-constexpr int VG_M = 128, VG_N = 64, VG_K = 16;
+}  // namespace
 
-__global__ void __launch_bounds__(256) ppph_slab_from_vertex_kernel(
-    const double* __restrict__ gre, const double* __restrict__ gim, int nf, int np, int z,
-    double* __restrict__ slab, Dims d) {
-  __shared__ double As[VG_K][VG_M + 1];
-  __shared__ double Bs[VG_K][VG_N + 1];
-  const int v = d.v, a0 = np - v;
-  const long long M = (long long)v * v;  // m = a + v*c
-  const long long m0 = (long long)blockIdx.x * VG_M;
-  const int n0 = blockIdx.y * VG_N;      // n = b
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
-  const int fr = lane >> 2, fk = lane & 3;
-  double acc[4][4][2] = {};
-  // global -> shared assignment: thread loads k = tid & 15 of rows (tid >> 4) + 16 r
-  const int lk = tid & 15, lr = tid >> 4;
-  size_t arow[VG_M / 16], brow[VG_N / 16];
-  bool aok[VG_M / 16], bok[VG_N / 16];
+constexpr int VG_BM = 64, VG_BN = 128, VG_STAGES = 4;
+constexpr int VG_STAGE_DBL = (VG_BM + VG_BN) * 16;                      // K = 16 per stage: 24 KB
+constexpr int VG_THREADS = 9 * 32;                                      // 8 consumer warps + 1 producer warp
+constexpr int VG_SMEM_BYTES = VG_STAGES * VG_STAGE_DBL * 8 + 2 * VG_STAGES * 8;
+
+// Gp[kc][r][kk] from G[F + nf (p + np q)] (Re, Im); rows r >= np^2 (padding) and K >= 2 nf are zero.
+// One thread per (r, kc): reads 4 consecutive F (coalesced across the kc-fastest thread index),
+// writes one 32-byte row.
+__global__ void __launch_bounds__(256) pack_vertex_kernel(const double* __restrict__ gre,
+                                                          const double* __restrict__ gim, int nf, long long nrows,
+                                                          long long rows_padded, int kp4, double* __restrict__ gp) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows_padded * kp4) return;
+  const int kc = (int)(gid % kp4);
+  const long long r = gid / kp4;
+  double out[4];
 #pragma unroll
-  for (int r = 0; r < VG_M / 16; ++r) {
-    const long long m = m0 + lr + 16 * r;
-    aok[r] = m < M;
-    const int a = aok[r] ? (int)(m % v) : 0, c = aok[r] ? (int)(m / v) : 0;
-    arow[r] = (size_t)nf * ((a0 + a) + (size_t)np * (a0 + c));
-  }
-#pragma unroll
-  for (int r = 0; r < VG_N / 16; ++r) {
-    const int b = n0 + lr + 16 * r;
-    bok[r] = b < v;
-    brow[r] = (size_t)nf * ((a0 + (bok[r] ? b : 0)) + (size_t)np * z);
-  }
-  for (int part = 0; part < 2; ++part) {
-    const double* G = part == 0 ? gre : gim;
-    for (int k0 = 0; k0 < nf; k0 += VG_K) {
-      const bool kok = k0 + lk < nf;
-#pragma unroll
-      for (int r = 0; r < VG_M / 16; ++r) As[lk][lr + 16 * r] = (kok && aok[r]) ? G[arow[r] + k0 + lk] : 0.0;
-#pragma unroll
-      for (int r = 0; r < VG_N / 16; ++r) Bs[lk][lr + 16 * r] = (kok && bok[r]) ? G[brow[r] + k0 + lk] : 0.0;
-      __syncthreads();
-#pragma unroll
-      for (int ks = 0; ks < VG_K; ks += 4) {
-        double af[4], bf[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) af[i] = As[ks + fk][wm + 8 * i + fr];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = Bs[ks + fk][wn + 8 * j + fr];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-      }
-      __syncthreads();
+  for (int kk = 0; kk < 4; ++kk) {
+    const int kf = 4 * kc + kk;
+    double x = 0.0;
+    if (r < nrows) {
+      if (kf < nf) x = gre[(size_t)r * nf + kf];
+      else if (kf < 2 * nf) x = gim[(size_t)r * nf + (kf - nf)];
     }
+    out[kk] = x;
   }
-  // C fragment: rows 8i + (lane>>2), columns 8j + 2 (lane&3) + {0,1}
+  double2* dst = reinterpret_cast<double2*>(gp + ((size_t)kc * rows_padded + r) * 4);
+  dst[0] = make_double2(out[0], out[1]);
+  dst[1] = make_double2(out[2], out[3]);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgParams p) {
+  extern __shared__ __align__(128) unsigned char vg_smem[];
+  double* ring = reinterpret_cast<double*>(vg_smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + VG_STAGES * VG_STAGE_DBL);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ring_u = vg_smem_u32(ring), full_u = vg_smem_u32(bars), empty_u = vg_smem_u32(bars + VG_STAGES);
+  if (tid == 0) {
+    for (int s = 0; s < VG_STAGES; ++s) {
+      vg_mbar_init(full_u + 8 * s, 1);
+      vg_mbar_init(empty_u + 8 * s, 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- which tile
+  const int mt = blockIdx.x, nt = blockIdx.y, batch = blockIdx.z;
+  // first vertex row of 16-row group g of the M tile (producer lane l copies group l & 3), of the N tile
+  const int g_ = lane & 3;
+  long long rowA, rowB;
+  long long outoff = 0;
+  int Q = 0, dc = 0;
+  if (MODE == VG_PACKED) {
+    Q = mt / p.nk4;
+    dc = mt - Q * p.nk4;
+    const int d = min(4 * dc + g_, p.v - 1);                     // padded d: clamped source, masked output
+    rowA = p.a_base + 16 * Q + (long long)p.np * (p.a0 + d);     // rows (b, d): G[., a0 + b, a0 + d]
+    rowB = p.b_base + (long long)VG_BN * nt;                     // rows (c, z): G[., a0 + c, z]
+  } else {
+    const int b0 = batch % p.nb0, b1 = batch / p.nb0;
+    const long long s0 = p.map0 ? p.map0[b0] : b0, s1 = p.map1 ? p.map1[b1] : b1;
+    rowA = p.a_base + p.a_s0 * s0 + p.a_s1 * s1 + (long long)VG_BM * mt + 16 * g_;
+    rowB = p.b_base + p.b_s0 * s0 + p.b_s1 * s1 + (long long)VG_BN * nt;
+    outoff = p.o_s0 * b0 + p.o_s1 * b1;
+  }
+  const int nstage = (p.kp4 + 3) >> 2;   // kp4 is a multiple of 4 (K padded to 16)
+
+  if (warp == 8) {
+    // ===== producer warp: lane l < 16 copies A group (l & 3) of K-chunk (l >> 2); lanes 16..19 the B chunk
+    const bool isA = lane < 16, act = lane < 20;
+    const int kcl = isA ? (lane >> 2) : (lane - 16);
+    const long long row = isA ? rowA : rowB;
+    const uint32_t bytes = isA ? 512u : 4096u;
+    const uint32_t soff = isA ? (uint32_t)((kcl * VG_BM + 16 * (lane & 3)) * 32) : (uint32_t)(VG_BM * 128 + kcl * VG_BN * 32);
+    const double* src = p.gp + (size_t)row * 4;
+    for (int s = 0; s < nstage; ++s) {
+      const int slot = s % VG_STAGES;
+      const uint32_t ph = (uint32_t)(s / VG_STAGES) & 1u;
+      vg_mbar_wait(empty_u + 8 * slot, ph ^ 1u);
+      if (lane == 0) vg_mbar_expect_tx(full_u + 8 * slot, (uint32_t)(VG_STAGE_DBL * 8));
+      __syncwarp();
+      if (act)
+        vg_bulk_g2s(ring_u + slot * (VG_STAGE_DBL * 8) + soff, src + (size_t)(4 * s + kcl) * (size_t)p.rows_padded * 4,
+                    bytes, full_u + 8 * slot);
+    }
+    return;
+  }
+
+  // ===== consumer warps: warp tile 32 x 32
+  const int wm = warp & 1, wn = warp >> 1;
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long m = m0 + wm + 8 * i + fr;
-    if (m >= M) continue;
-    const int a = (int)(m % v), c = (int)(m / v);
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int s = 0; s < nstage; ++s) {
+    const int slot = s % VG_STAGES;
+    const uint32_t ph = (uint32_t)(s / VG_STAGES) & 1u;
+    vg_mbar_wait(full_u + 8 * slot, ph);
+    const double* As = ring + slot * VG_STAGE_DBL + 32 * wm * 4 + lane;
+    const double* Bs = ring + slot * VG_STAGE_DBL + VG_BM * 16 + 32 * wn * 4 + lane;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int b = n0 + wn + 8 * j + 2 * fk + e;
-        if (b < v) slab[a + (size_t)v * (b + (size_t)v * c)] = acc[i][j][e];
-      }
+    for (int kc = 0; kc < 4; ++kc) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = As[kc * VG_BM * 4 + 32 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Bs[kc * VG_BN * 4 + 32 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncwarp();
+    if (lane == 0) vg_mbar_arrive(empty_u + 8 * slot);
+  }
+
+  // ---- output.  C fragment (i, j): rows 8 i + (lane >> 2), columns 8 j + 2 (lane & 3) + {0, 1}
+  const int g = lane >> 2, t2 = 2 * (lane & 3);
+  if (MODE == VG_PACKED) {
+    // tile row m = 16 kk + bl (kk = d - 4 dc), tile column n = c - 128 nt
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = 32 * wm + 8 * i + g, kk = m >> 4, bl = m & 15;
+      const bool mok = (16 * Q + bl < p.v) && (4 * dc + kk < p.v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = VG_BN * nt + 32 * wn + 8 * j + t2 + e;
+          const int R = c >> 4, cl = c & 15;
+          if (R < p.nr)
+            p.out[((size_t)(Q * p.nr + R) * p.nk4 + dc) * 1024 + (size_t)(16 * bl + cl) * 4 + kk] =
+                (mok && c < p.v) ? acc[i][j][e] : 0.0;
+        }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = VG_BM * mt + 32 * wm + 8 * i + g;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = VG_BN * nt + 32 * wn + 8 * j + t2 + e;
+          if (n < p.N) p.out[outoff + (long long)m * p.sm + (long long)n * p.sn] = acc[i][j][e];
+        }
+    }
   }
 }
 
-static inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
+// fixed-order second pass of the (T) energy: E_t = sum over the orbits of triple t of the per-item
+// partial sums the fused kernel wrote -- bitwise reproducible for any grid size / CTA timing.
+__global__ void __launch_bounds__(256) reduce_items_kernel(const double* __restrict__ e_item, int ntriples,
+                                                           int norbits, int order, double* __restrict__ e_triple) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntriples) return;
+  double s = 0.0;
+  if (order == 0) {
+    const double* q = e_item + (size_t)t * norbits;
+    for (int orb = 0; orb < norbits; ++orb) s += q[orb];
+  } else {
+    for (int orb = 0; orb < norbits; ++orb) s += e_item[(size_t)orb * ntriples + t];
+  }
+  e_triple[t] = s;
+}
+
 
 cudaError_t launch_pack_vt_slab(const double* raw_slab, double* vt_slab, Dims d, cudaStream_t s) {
   dim3 grid(d.nk4, d.nr * d.nr);
@@ -243,9 +390,9 @@ cudaError_t launch_pack_t2h(const double* t2, double* t2h, Dims d, cudaStream_t 
   pack_t2h_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(t2, t2h, d);
   return cudaGetLastError();
 }
-cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, cudaStream_t s) {
+cudaError_t launch_pack_ut(const double* hhhp, double* ut, Dims d, const int* hmap, cudaStream_t s) {
   const size_t rows = (size_t)d.o * d.o * d.nr * d.nl4 * 16;
-  pack_ut_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(hhhp, ut, d);
+  pack_ut_kernel<<<blocks_for(rows, 256), 256, 0, s>>>(hhhp, ut, d, hmap);
   return cudaGetLastError();
 }
 cudaError_t launch_pphh_symsum(const double* pphh, double* qsum, Dims d, cudaStream_t s) {
@@ -254,11 +401,32 @@ cudaError_t launch_pphh_symsum(const double* pphh, double* qsum, Dims d, cudaStr
   pphh_symsum_kernel<<<grid, 256, 0, s>>>(pphh, qsum, d);
   return cudaGetLastError();
 }
-cudaError_t launch_ppph_slab_from_vertex(const double* gre, const double* gim, int nf, int np,
-                                         int z, double* raw_slab, Dims d, cudaStream_t s) {
-  const long long M = (long long)d.v * d.v;
-  dim3 grid((unsigned)((M + VG_M - 1) / VG_M), (unsigned)((d.v + VG_N - 1) / VG_N));
-  ppph_slab_from_vertex_kernel<<<grid, 256, 0, s>>>(gre, gim, nf, np, z, raw_slab, d);
+cudaError_t vertex_gemm_configure() {
+  cudaError_t e = cudaFuncSetAttribute(vertex_gemm_kernel<VG_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       VG_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(vertex_gemm_kernel<VG_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, VG_SMEM_BYTES);
+}
+cudaError_t launch_pack_vertex(const double* gre, const double* gim, int nf, int np, double* gp, cudaStream_t s) {
+  const long long nrows = (long long)np * np, rp = vertex_rows_padded(np);
+  const int kp4 = vertex_kp4(nf);
+  pack_vertex_kernel<<<blocks_for((size_t)rp * kp4, 256), 256, 0, s>>>(gre, gim, nf, nrows, rp, kp4, gp);
+  return cudaGetLastError();
+}
+cudaError_t launch_vertex_gemm(const VgParams& p, cudaStream_t s) {
+  if (p.mode == VG_PACKED) {
+    dim3 grid((unsigned)(p.nr * p.nk4), (unsigned)((p.nr * 16 + VG_BN - 1) / VG_BN), 1);
+    vertex_gemm_kernel<VG_PACKED><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
+  } else {
+    dim3 grid((unsigned)((p.M + VG_BM - 1) / VG_BM), (unsigned)((p.N + VG_BN - 1) / VG_BN), (unsigned)(p.nb0 * p.nb1));
+    vertex_gemm_kernel<VG_STRIDED><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_reduce_items(const double* e_item, int ntriples, int norbits, int order, double* e_triple,
+                                cudaStream_t s) {
+  if (ntriples <= 0) return cudaSuccess;
+  reduce_items_kernel<<<blocks_for((size_t)ntriples, 256), 256, 0, s>>>(e_item, ntriples, norbits, order, e_triple);
   return cudaGetLastError();
 }
 

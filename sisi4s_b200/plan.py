@@ -12,9 +12,10 @@ readers/writers and the triples step:
 
     python -m sisi4s_b200 in.yaml        (cwd-relative file names, like the reference)
 
-Algorithms that produce the inputs by computation (Hartree-Fock, integral transformation, the
-CCSD solver) are out of scope; a plan naming one of them fails with the
-reference's behaviour for an unknown algorithm made explicit.
+The steps next to the path are registered further down: UegVertexGenerator,
+CoulombIntegralsFromVertex (N1) and CcsdEnergyFromCoulombIntegrals[Reference] (N3).  Hartree-Fock and
+the Gaussian integral engines stay out of scope; a plan naming an unknown algorithm fails with the
+reference's behaviour for an unknown name made explicit.
 """
 from __future__ import annotations
 

@@ -56,21 +56,33 @@ class TriplesEngine:
     """One GPU's (T) engine: owns a ``pt_handle_t``."""
 
     def __init__(self, o: int, v: int, device: int = 0, engine: int = _lib.PT_ENGINE_FUSED,
-                 keep_raw: bool = False, grid: int = 0, slab_slots: int = 0, o_all: int | None = None):
+                 keep_raw: bool = False, grid: int = 0, slab_slots: int = 0, o_all: int | None = None,
+                 hole_block: int = 0, async_upload: bool = False, pin_host: bool = False):
         """``o_all`` > ``o``: engine for a hole subset of a larger problem (pt_create_ex): ``o`` active
-        holes (those of the triples that are run), ``o_all`` holes in the hole contraction."""
+        holes (those of the triples that are run), ``o_all`` holes in the hole contraction.
+        ``hole_block`` = b: out-of-core mode of the library (BASELINE configs[4]): the setters take the
+        full tensors, T2 / PPHH / PPPH stay in host memory (kept alive by this object) and are staged
+        per hole-block group of <= 3b active holes."""
         self.lib = _lib.load()
         self.o, self.v = int(o), int(v)
         self.o_all = self.o if o_all is None else int(o_all)
         self._h = C.c_void_p()
         _lib.check(self.lib.pt_create_ex(C.byref(self._h), self.o, self.o_all, self.v, int(device)))
+        self._keepalive = []
+        self.hole_block = int(hole_block)
+        if hole_block:
+            self.set_option("hole_block", int(hole_block))   # first: it re-dimensions the device buffers
+        if async_upload:
+            self.set_option("async_upload", 1)
+        if pin_host:
+            self.set_option("pin_host", 1)
+        self.async_upload = bool(async_upload)
         self.set_option("keep_raw", int(keep_raw))
         self.set_option("engine", int(engine))
         if grid:
             self.set_option("grid", int(grid))
         if slab_slots:
             self.set_option("slab_slots", int(slab_slots))
-        self._keepalive = []
 
     # -- lifecycle
     def close(self):
@@ -93,46 +105,58 @@ class TriplesEngine:
     def set_option(self, key: str, value: int):
         _lib.check(self.lib.pt_set_option(self._h, key.encode(), int(value)))
 
+    def sync(self):
+        """Wait for the uploads / packing the setters enqueued (async_upload)."""
+        _lib.check(self.lib.pt_sync(self._h))
+
+    def _hold(self, a):
+        # host buffers the library may still read after the setter returns
+        if self.async_upload or self.hole_block:
+            self._keepalive.append(a)
+        return a
+
     # -- inputs
     def _shape(self, a, shape, name):
         if tuple(a.shape) != tuple(shape):
             raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
 
     def set_eigenenergies(self, epsi, epsa):
-        epsi, epsa = _f64(epsi), _f64(epsa)
+        epsi, epsa = self._hold(_f64(epsi)), self._hold(_f64(epsa))
         self._shape(epsi, (self.o,), "HoleEigenEnergies")
         self._shape(epsa, (self.v,), "ParticleEigenEnergies")
         _lib.check(self.lib.pt_set_eigenenergies(self._h, _ptr(epsi), _ptr(epsa)))
 
     def set_singles(self, t1):
-        t1 = _f64(t1)
+        t1 = self._hold(_f64(t1))
         self._shape(t1, (self.v, self.o), "CcsdSinglesAmplitudes")
         _lib.check(self.lib.pt_set_singles(self._h, _ptr(t1)))
 
     def set_doubles(self, t2):
-        t2 = _f64(t2)
+        t2 = self._hold(_f64(t2))
         self._shape(t2, (self.v, self.v, self.o, self.o), "CcsdDoublesAmplitudes")
         _lib.check(self.lib.pt_set_doubles(self._h, _ptr(t2)))
 
     def set_doubles_hole(self, t2_xl):
         """Hole-term doubles T2[a,b,x,l], x active / l all holes (pt_create_ex engines only)."""
-        t2_xl = _f64(t2_xl)
+        t2_xl = self._hold(_f64(t2_xl))
         self._shape(t2_xl, (self.v, self.v, self.o, self.o_all), "CcsdDoublesAmplitudes (hole term)")
         _lib.check(self.lib.pt_set_doubles_hole(self._h, _ptr(t2_xl)))
 
     def set_pphh(self, vabij):
-        vabij = _f64(vabij)
+        vabij = self._hold(_f64(vabij))
         self._shape(vabij, (self.v, self.v, self.o, self.o), "PPHHCoulombIntegrals")
         _lib.check(self.lib.pt_set_pphh(self._h, _ptr(vabij)))
 
     def set_hhhp(self, vijka):
-        vijka = _f64(vijka)
+        vijka = self._hold(_f64(vijka))
         self._shape(vijka, (self.o, self.o, self.o_all, self.v), "HHHPCoulombIntegrals")
         _lib.check(self.lib.pt_set_hhhp(self._h, _ptr(vijka)))
 
     def set_ppph(self, vabci, slabs_per_call: int = 0):
-        vabci = _f64(vabci)
+        vabci = self._hold(_f64(vabci))
         self._shape(vabci, (self.v, self.v, self.v, self.o), "PPPHCoulombIntegrals")
+        if self.hole_block:
+            return self.set_ppph_host(vabci)
         step = slabs_per_call or self.o
         slab = self.v ** 3
         flat = vabci.reshape(-1, order="F")
@@ -155,19 +179,38 @@ class TriplesEngine:
         nf, np_, np2 = g.shape
         if np_ != np2:
             raise ValueError("CoulombVertex must be [NF,Np,Np]")
-        gre, gim = _f64(g.real), _f64(g.imag)
+        gre, gim = self._hold(_f64(g.real)), self._hold(_f64(g.imag))
         _lib.check(self.lib.pt_set_vertex(self._h, nf, np_, _ptr(gre), _ptr(gim)))
 
+    def use_vertex_integrals(self):
+        """PPHH and HHHP built on the device from the resident vertex (after set_vertex) and used as
+        the step's inputs: the CoulombVertex contract then needs neither tensor from the host."""
+        _lib.check(self.lib.pt_use_vertex_integrals(self._h))
+
+    def vertex_integrals(self, block: str) -> np.ndarray:
+        """One real integral block ("PPHH", "HHHP", "PPPH") from the resident vertex, computed on the
+        device (CoulombIntegralsFromVertex.cxx:402-403, 416-417, 430-431), column-major."""
+        o, v = self.o_all, self.v
+        shape = {"PPHH": (v, v, o, o), "HHHP": (o, o, o, v), "PPPH": (v, v, v, o)}[block]
+        out = np.zeros(shape, dtype=np.float64, order="F")
+        _lib.check(self.lib.pt_vertex_integrals(self._h, block.encode(), _ptr(out)))
+        return out
+
     def set_inputs(self, epsi, epsa, T1, T2, Vpphh, Vhhhp, Vppph=None, vertex=None):
+        """``Vpphh`` / ``Vhhhp`` None with a vertex: both are built on the device from it."""
         self.set_eigenenergies(epsi, epsa)
         self.set_singles(T1)
         self.set_doubles(T2)
-        self.set_pphh(Vpphh)
-        self.set_hhhp(Vhhhp)
+        if Vpphh is not None:
+            self.set_pphh(Vpphh)
+        if Vhhhp is not None:
+            self.set_hhhp(Vhhhp)
         if Vppph is not None:
             self.set_ppph(Vppph)
         elif vertex is not None:
             self.set_vertex(vertex)
+            if Vpphh is None and Vhhhp is None:
+                self.use_vertex_integrals()
         else:
             raise ValueError("Missing argument: PPPHCoulombIntegrals (or CoulombVertex)")
 
@@ -208,6 +251,13 @@ class TriplesEngine:
         out = np.zeros(16 * 16 * 16, dtype=np.float64)
         _lib.check(self.lib.pt_debug_w_tile(self._h, x, y, z, ra, rb, rc, _ptr(out)))
         return out.reshape((16, 16, 16), order="F")
+
+    def bench_vertex_gemm(self, what: int, reps: int = 3):
+        """(seconds per build, algorithmic FLOP) of the integrals-from-vertex GEMM: 0 = one packed PPPH
+        slab, 1 = the PPHH block."""
+        s, f = C.c_double(), C.c_double()
+        _lib.check(self.lib.pt_bench_vertex_gemm(self._h, what, reps, C.byref(s), C.byref(f)))
+        return float(s.value), float(f.value)
 
     def bench_fp64(self, mode: int, warps_per_sm: int, iters: int):
         tf, mhz = C.c_double(), C.c_double()
@@ -328,17 +378,30 @@ class CcsdPerturbativeTriples(Algorithm):
     def make_engine(self) -> TriplesEngine:
         o, v, epsi, epsa = self._gather()
         engine = self.getIntegerArgument("engine", _lib.PT_ENGINE_FUSED)
+        # slabSlots / holeBlock: the memory options of the C++ plugin (CcsdPerturbativeTriplesGpu.cxx)
         eng = TriplesEngine(o, v, device=self.getIntegerArgument("device", 0), engine=engine,
-                            keep_raw=(engine == _lib.PT_ENGINE_NAIVE))
+                            keep_raw=(engine == _lib.PT_ENGINE_NAIVE),
+                            slab_slots=self.getIntegerArgument("slabSlots", 0),
+                            hole_block=self.getIntegerArgument("holeBlock", 0),
+                            async_upload=bool(self.getIntegerArgument("asyncUpload", 1)))
         eng.set_eigenenergies(epsi, epsa)
         eng.set_singles(self.getTensorArgument("CcsdSinglesAmplitudes"))
         eng.set_doubles(self.getTensorArgument("CcsdDoublesAmplitudes"))
-        eng.set_pphh(self.getTensorArgument("PPHHCoulombIntegrals"))
-        eng.set_hhhp(self.getTensorArgument("HHHPCoulombIntegrals"))
+        have_vertex = self.isArgumentGiven("CoulombVertex") and not self.isArgumentGiven("PPPHCoulombIntegrals")
+        from_vertex = have_vertex and bool(self.getIntegerArgument("integralsFromVertex", 0))
+        if not from_vertex:
+            eng.set_pphh(self.getTensorArgument("PPHHCoulombIntegrals"))
+            eng.set_hhhp(self.getTensorArgument("HHHPCoulombIntegrals"))
         if self.isArgumentGiven("PPPHCoulombIntegrals"):
-            eng.set_ppph(self.getTensorArgument("PPPHCoulombIntegrals"))
-        elif self.isArgumentGiven("CoulombVertex"):
+            ppph = self.getTensorArgument("PPPHCoulombIntegrals")
+            if eng.hole_block or self.getIntegerArgument("slabSlots", 0):
+                eng.set_ppph_host(ppph)
+            else:
+                eng.set_ppph(ppph)
+        elif have_vertex:
             eng.set_vertex(self.getTensorArgument("CoulombVertex"))
+            if from_vertex:       # PPHH / HHHP on the device too (CoulombIntegralsFromVertex.cxx:402-403,416-417)
+                eng.use_vertex_integrals()
         else:
             raise SisiException("Missing argument: PPPHCoulombIntegrals")
         return eng
@@ -348,7 +411,7 @@ class CcsdPerturbativeTriples(Algorithm):
             res = eng.run()
             self.stats = eng.stats()
         e_triples = res.energy
-        e_ccsd = self.getRealArgument("CcsdEnergy", 0.0)
+        e_ccsd = self.getRealArgument("CcsdEnergy")   # mandatory, as :241 / PerturbativeTriples.cxx:229
         e = e_ccsd + e_triples
         self.log = {"e": e, "ccsd": e_ccsd, "triples": e_triples}  # LOG lines of :243-245
         given = [k for k in self.OUT_KEYS if self.isArgumentGiven(k)]
@@ -359,13 +422,12 @@ class CcsdPerturbativeTriples(Algorithm):
         return e
 
     def dryRun(self):
-        """Memory estimate (reference :250-284 counts 8 live v^3 CTF tensors); here: device bytes."""
+        """Memory estimate.  The reference (:250-284) counts its 8 live v^3 CTF tensors plus the
+        sliced inputs; the GPU step reports the device bytes per GPU instead, computed by the
+        library itself (pt_estimate_device_bytes: the same formula the C++ plugin logs)."""
         o, v, _, _ = self._gather()
-        nr = (v + 15) // 16
-        nk4, nl4 = (v + 3) // 4, (o + 3) // 4
-        packed = o * nr * nr * nk4 * 1024 + 2 * o * o * nr * 64 * max(nk4, 1) + o * nr * nr * nl4 * 1024
-        raw = 2 * v * v * o * o + v * o + v ** 3          # PPHH + its pre-added pair sums, T1, one slab stage
-        self.dry_bytes = 8 * (packed + raw)
+        slots = self.getIntegerArgument("slabSlots", 0)
+        self.dry_bytes = int(_lib.load().pt_estimate_device_bytes(o, v, slots, self.getIntegerArgument("holeBlock", 0)))
         return self.dry_bytes
 
 

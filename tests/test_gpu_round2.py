@@ -1,0 +1,201 @@
+"""GPU tests added in round 2 (all through the C ABI):
+
+* the metric's own shapes against the C oracle: sampled sorted triples of every hole class at
+  BASELINE configs[2] (o=40, v=300) and -- marked slow -- configs[3] (o=64, v=512);
+* bitwise reproducibility of the per-triple energies (fixed-order second pass);
+* integrals from the vertex on the device against the NumPy restatement of
+  CoulombIntegralsFromVertex.cxx:402-403, 416-417, 430-431;
+* the in-library hole-block mode (BASELINE configs[4] path) against the oracle and the resident run;
+* the dryRun estimate against the bytes the handle really holds; asynchronous setters.
+"""
+import numpy as np
+import pytest
+
+from sisi4s_b200 import _lib
+from sisi4s_b200 import synthetic as S
+from sisi4s_b200.triples import CcsdPerturbativeTriples, TriplesEngine
+
+pytestmark = pytest.mark.gpu
+ABS_TOL = 1e-9
+
+
+def _triples(o):
+    return [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)]
+
+
+# ------------------------------------------------------------ parity at the metric's own shapes
+def test_o40_v300_sampled_triples_match_c_oracle():
+    """BASELINE configs[2] -- the shape the metric is quoted on -- CUDA path vs oracle/pt_oracle.c on
+    sampled sorted triples covering all four hole classes (i<j<k, i=j<k, i<j=k, i=j=k)."""
+    from oracle import c_oracle as CO
+    o, v = 40, 300
+    inp = S.make_inputs(o, v, seed=2026, kind="vertex", nf=24)
+    tr = _triples(o)
+    picks = [tr.index(t) for t in ((0, 1, 2), (3, 17, 39), (20, 21, 22), (11, 30, 38), (0, 0, 1), (12, 12, 30),
+                                   (0, 1, 1), (7, 25, 25), (39, 39, 39), (5, 5, 5))]
+    with TriplesEngine(o, v) as eng:
+        eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph)
+        got = eng.run_list(picks).per_triple
+        again = eng.run_list(picks[::-1]).per_triple[::-1]
+    CO.use_blas(True)
+    ref = CO.triples_list(*inp.args(), np.array(picks))
+    assert np.abs(got - ref).max() <= ABS_TOL, (got, ref)
+    assert np.array_equal(got, again)               # bitwise, whatever the launch order
+    # the synthetic scale: |E_t| of a generic triple ~ 1e-5 .. 1e-4 Eh, so 1e-9 abs is a 1e-5 relative bar
+    assert 1e-8 < np.abs(ref[:4]).max() < 1e-2
+
+
+@pytest.mark.slow
+def test_o64_v512_sampled_triples_match_c_oracle():
+    """BASELINE configs[3] shape (105 GB resident, PPPH built on the device from the vertex): sampled
+    triples vs the C oracle, which is handed only the PPPH slabs of the sampled triples."""
+    from oracle import c_oracle as CO
+    o, v = 64, 512
+    inp = S.make_inputs(o, v, seed=2026, kind="vertex", nf=24, with_ppph=False)
+    tr = _triples(o)
+    trip = ((3, 17, 40), (5, 5, 30), (7, 21, 21))
+    picks = [tr.index(t) for t in trip]
+    with TriplesEngine(o, v) as eng:
+        eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, vertex=inp.Gamma)
+        got = eng.run_list(picks).per_triple
+    CO.use_blas(True)
+    ref = CO.triples_list_blocks(inp.epsi, inp.epsa, inp.T1, inp.T2, lambda j, k: inp.Vpphh[:, :, j, k], inp.Vhhhp,
+                                 lambda z: S.ppph_slab_from_vertex(inp.Gamma, o, v, z), np.array(picks))
+    assert np.abs(got - ref).max() <= ABS_TOL, (got, ref)
+
+
+# ------------------------------------------------------------ reproducibility
+def test_per_triple_energies_are_bitwise_reproducible():
+    """E_t is a fixed-order sum of per-item partial sums: identical bits for repeated runs, any grid
+    size, any item order of the launch."""
+    inp = S.make_inputs(6, 40, seed=4, kind="random")
+    with TriplesEngine(6, 40) as eng:
+        eng.set_inputs(*inp.args())
+        base = eng.run().per_triple
+        assert np.array_equal(eng.run().per_triple, base)
+        for opts in ({"grid": 7}, {"grid": 33}, {"class_sort": 0}, {"item_sync": 1}):
+            for k, val in opts.items():
+                eng.set_option(k, val)
+            assert np.array_equal(eng.run().per_triple, base), opts
+            for k in opts:
+                eng.set_option(k, {"grid": 0, "class_sort": 1, "item_sync": 0}[k])
+
+
+# ------------------------------------------------------------ integrals from the vertex (N1)
+@pytest.mark.parametrize("o,v,nf", [(5, 19, 38), (7, 20, 9), (3, 70, 24), (12, 33, 50)])
+def test_vertex_integrals_match_numpy(o, v, nf):
+    """PPHH / HHHP / PPPH from the vertex on the FP64 tensor pipe (pt_vertex_integrals) vs the NumPy
+    restatement of the reference's index strings; nf not a multiple of 8, v not a multiple of 16/64."""
+    gamma = S.make_vertex(o, v, seed=17, nf=nf, kappa=1.0)
+    vpphh, vhhhp, vppph = S.integrals_from_vertex(gamma, o, v)
+    with TriplesEngine(o, v) as eng:
+        eng.set_vertex(gamma)
+        for name, want in (("PPHH", vpphh), ("HHHP", vhhhp), ("PPPH", vppph)):
+            got = eng.vertex_integrals(name)
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 1e-13 * max(1.0, np.abs(want).max()), name
+
+
+def test_vertex_only_contract_needs_no_host_integrals():
+    """CoulombVertex contract with PPHH / HHHP built on the device too (pt_use_vertex_integrals)."""
+    from oracle import pt_oracle as O
+    inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
+    e_ref, per_ref = O.triples_loop(*inp.args(), return_per_triple=True)
+    with TriplesEngine(5, 19) as eng:
+        eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, None, None, vertex=inp.Gamma)
+        res = eng.run()
+    assert abs(res.energy - e_ref) <= ABS_TOL
+    assert np.abs(res.per_triple - per_ref).max() <= ABS_TOL
+    # the same through the plugin mirror: integralsFromVertex: 1
+    data = dict(HoleEigenEnergies=inp.epsi, ParticleEigenEnergies=inp.epsa, CcsdEnergy=inp.ccsd_energy,
+                CcsdSinglesAmplitudes=inp.T1, CcsdDoublesAmplitudes=inp.T2, CoulombVertex=inp.Gamma)
+    args = {k: "$" + k for k in data}
+    args.update(integralsFromVertex=1, CcsdPerturbativeTriplesEnergy="$E")
+    CcsdPerturbativeTriples(args, data).run()
+    assert abs(data["E"] - (inp.ccsd_energy + e_ref)) <= ABS_TOL
+
+
+# ------------------------------------------------------------ hole-block mode (configs[4] path)
+@pytest.mark.parametrize("block,source", [(1, "ppph"), (2, "ppph"), (2, "vertex"), (3, "vertex_only"), (8, "ppph")])
+def test_hole_block_mode_equals_oracle(block, source):
+    """pt_set_option("hole_block", b): T2 / PPHH / PPPH stay in host memory, the library walks the
+    triples by hole-block groups with buffers allocated once.  Per-triple energies vs the oracle,
+    partial ranges, explicit lists."""
+    from oracle import pt_oracle as O
+    o, v = 7, 20
+    inp = S.make_inputs(o, v, seed=17, kind="vertex")
+    e_ref, per_ref = O.triples_loop(*inp.args(), return_per_triple=True)
+    with TriplesEngine(o, v, hole_block=block) as eng:
+        if source == "ppph":
+            eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph)
+        elif source == "vertex":
+            eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, vertex=inp.Gamma)
+        else:
+            eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, None, None, vertex=inp.Gamma)
+        res = eng.run()
+        st = eng.stats()
+        assert abs(res.energy - e_ref) <= ABS_TOL
+        assert np.abs(res.per_triple - per_ref).max() <= ABS_TOL
+        assert st.groups_staged >= 1
+        b, e = eng.partition(3, 1)
+        part = eng.run(b, e)
+        assert np.abs(part.per_triple - per_ref[b:e]).max() <= ABS_TOL
+        pick = [40, 3, 77, 12]
+        lst = eng.run_list(pick)
+        assert np.abs(lst.per_triple - per_ref[pick]).max() <= ABS_TOL
+
+
+def test_hole_block_mode_is_bitwise_the_resident_run():
+    """Unsymmetric random inputs: the staged sub-problem computes the same bits as the resident one."""
+    inp = S.make_inputs(9, 37, seed=2026, kind="random")
+    with TriplesEngine(9, 37) as eng:
+        eng.set_inputs(*inp.args())
+        base = eng.run().per_triple
+    for block in (2, 4):
+        with TriplesEngine(9, 37, hole_block=block) as eng:
+            eng.set_inputs(*inp.args())
+            got = eng.run().per_triple
+        assert np.array_equal(got, base), block
+
+
+def test_hole_block_option_order_is_checked():
+    inp = S.make_inputs(4, 18, seed=4, kind="random")
+    with TriplesEngine(4, 18) as eng:
+        eng.set_eigenenergies(inp.epsi, inp.epsa)
+        with pytest.raises(_lib.PtError, match="hole_block must be set before"):
+            eng.set_option("hole_block", 2)
+
+
+# ------------------------------------------------------------ dryRun, async setters
+@pytest.mark.parametrize("o,v,kw", [(12, 70, {}), (12, 70, {"slab_slots": 6}), (12, 70, {"hole_block": 2})])
+def test_dry_run_estimate_matches_device_bytes(o, v, kw):
+    """dryRun (reference CcsdPerturbativeTriples.cxx:250-284 reports a memory estimate): the number the
+    plugin reports = pt_estimate_device_bytes, within 5 % of what the handle really holds."""
+    inp = S.make_inputs(o, v, seed=17, kind="vertex", nf=12)
+    with TriplesEngine(o, v, **kw) as eng:
+        eng.set_eigenenergies(inp.epsi, inp.epsa); eng.set_singles(inp.T1); eng.set_doubles(inp.T2)
+        eng.set_pphh(inp.Vpphh); eng.set_hhhp(inp.Vhhhp)
+        eng.set_ppph_host(inp.Vppph)
+        eng.run(0, 20)
+        held = eng.stats().device_bytes
+    est = _lib.load().pt_estimate_device_bytes(o, v, kw.get("slab_slots", 0), kw.get("hole_block", 0))
+    assert abs(est - held) <= 0.05 * held, (est, held)
+    data = dict(HoleEigenEnergies=inp.epsi, ParticleEigenEnergies=inp.epsa)
+    args = {k: "$" + k for k in data}
+    if "slab_slots" in kw:
+        args["slabSlots"] = kw["slab_slots"]
+    if "hole_block" in kw:
+        args["holeBlock"] = kw["hole_block"]
+    assert CcsdPerturbativeTriples(args, data).dryRun() == est
+
+
+def test_async_setters_give_the_same_energy():
+    inp = S.make_inputs(5, 19, seed=2026, kind="vertex")
+    with TriplesEngine(5, 19) as eng:
+        eng.set_inputs(*inp.args())
+        base = eng.run()
+    with TriplesEngine(5, 19, async_upload=True) as eng:
+        eng.set_inputs(*inp.args())
+        res = eng.run()          # pt_run waits for the enqueued uploads itself
+        assert eng.stats().seconds_upload > 0
+    assert np.array_equal(res.per_triple, base.per_triple)

@@ -2,7 +2,7 @@
 """Generate the step / routing tables of the fused (T) kernel and emulate its
 data flow on the CPU.
 
-The fused kernel (sisi4s_b200/csrc/pt_fused.cuh) processes one *work item* =
+The fused kernel (sisi4s_b200/csrc/pt_fused.cu) processes one *work item* =
 (sorted hole triple i<=j<=k, orbit {A>=B>=C} of 16-wide particle ranges).  For
 that item it runs a short list of *stacked GEMM steps*; each step multiplies up
 to two 16-row T2 panels against ONE shared 256-pair tile of a PPPH slab, and
