@@ -2,22 +2,31 @@
 """Benchmark of the (T) hot path (BASELINE.json metric: FP64 TFLOP/s and wall-s at
 o=40, v=300 on 1/2/4/8 B200, next to the CPU path).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload: synthetic UEG-style closed-shell inputs at o=40, v=300 (BASELINE configs[2]),
-11 GB of integrals/amplitudes per GPU (replicated), far larger than the 126 MB L2.
-One STEP = one weight-balanced contiguous eighth of the sorted-triple list
-(i<=j<=k, reference enumeration order) processed by one `pt_run` per rank; eight
-consecutive steps = one complete E(T).  With N ranks every step's eighth is split
-N ways (pt_partition), so the total work is fixed: strong scaling.  The only
-communication is one all-reduce of the scalar energy (and of the timings).
+Workloads (synthetic UEG-style closed-shell inputs, sisi4s_b200/synthetic.py conventions):
 
-`value` = algorithmic FLOP (2 v^3 (v+o) per ordered hole triple) of the timed steps
-of all ranks / max-over-ranks device time, inputs already resident in HBM.
-`e2e` = the same metric through the plugin-level API (sisi4s_b200.triples.
-CcsdPerturbativeTriples.run): host buffers -> H2D copies + packing + all triples
-+ D2H of the energy, timed on the host around the call.
+  o40v300  (default; BASELINE configs[2], the configuration the metric is quoted on) 11 GB of
+           integrals / amplitudes per GPU, replicated.  One STEP = one weight-balanced contiguous
+           eighth of the sorted-triple list (i<=j<=k, reference enumeration order), split over the
+           ranks with pt_partition; eight steps = one complete E(T).
+  o20v100  (configs[1])  one step = the complete E(T).
+  o64v512  (configs[3])  105 GB resident per GPU, PPPH built on the device from the vertex; one
+           step = 1/256 of the list; e2e = one complete E(T) at 8 GPUs (a 1/world... share at fewer).
+  o100v800 (configs[4])  hole-block mode of the library (T2 in host memory, PPHH / PPPH rebuilt from
+           the resident vertex per group); one step = one generic hole-block group (216 sorted
+           triples, 1296 W blocks) per rank -- a weight-balanced sample of the 9.2e17-FLOP problem.
+
+Total work per step is fixed and split over the ranks: strong scaling.  The only data collective
+is one all-reduce of the scalar energy (and of the timings).
+
+`value` = algorithmic FLOP (2 v^3 (v+o) per ordered hole triple) of the timed steps of all ranks /
+max-over-ranks device time (CUDA events on the library's stream), inputs resident in HBM.
+`e2e` = the same metric through the plugin-level API (sisi4s_b200.triples.CcsdPerturbativeTriples):
+pinned host buffers -> H2D copies + packing + triples + D2H of the energy, timed on the host.
+`parity` = sampled sorted triples of THIS workload, CUDA path vs the C oracle, |dE_t| <= 1e-9 Eh
+(exit code 1 otherwise); `cpu_baseline` = the oracle's time on the same triples.
 """
 from __future__ import annotations
 
@@ -42,26 +51,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-O_, V_ = 40, 300
-NBATCH = 8
 NF_SYNTH = 24  # auxiliary index of the synthetic vertex (setup cost only; not on the timed path)
-# --workload: (o, v, steps per complete E(T), PPPH on the host?, BASELINE.json config)
+TOL = 1e-9     # Eh, absolute (BASELINE.json north_star)
 WORKLOADS = {
-    "o40v300": (40, 300, 8, True, "configs[2]"),     # the configuration the metric is quoted on (default)
-    "o20v100": (20, 100, 1, True, "configs[1]"),
-    "o64v512": (64, 512, 64, False, "configs[3]"),   # 96.6 GB per GPU; PPPH built on the device from the vertex
+    "o40v300": dict(o=40, v=300, nbatch=8, ppph_host=True, config="configs[2]", mode="resident"),
+    "o20v100": dict(o=20, v=100, nbatch=1, ppph_host=True, config="configs[1]", mode="resident"),
+    "o64v512": dict(o=64, v=512, nbatch=256, ppph_host=False, config="configs[3]", mode="resident"),
+    "o100v800": dict(o=100, v=800, block=6, ppph_host=False, config="configs[4]", mode="hole_block"),
 }
-HOST_PPPH = True
-CONFIG_NAME = "configs[2]"
 
 
 def flops_of(o, v, weight):
     return 2.0 * v ** 3 * (v + o) * weight
 
 
+def sorted_triples(o):
+    return [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)]
+
+
 def triple_weights(o):
-    return np.array([[6, 3, 3, 1][(i == j) + 2 * (j == k)]
-                     for i in range(o) for j in range(i, o) for k in range(j, o)], dtype=np.int64)
+    return np.array([[6, 3, 3, 1][(i == j) + 2 * (j == k)] for i, j, k in sorted_triples(o)], dtype=np.int64)
 
 
 class ClockSampler:
@@ -121,7 +130,7 @@ def measure_fp64_peak(device):
     torch.matmul(a, b)
     torch.cuda.synchronize(device)
     best = 0.0
-    t_end = time.time() + 4.0
+    t_end = time.time() + 3.0
     rates = []
     while time.time() < t_end:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -133,70 +142,218 @@ def measure_fp64_peak(device):
     return best, float(np.median(rates[len(rates) // 2:]))
 
 
-def pinned_like(arr):
-    """Copy a numpy array into page-locked host memory, same shape / Fortran order."""
+# --------------------------------------------------------------------------------------------
+# host buffers of the large tensors: page-locked, private per rank or -- for the shapes whose
+# tensors would not fit N times into the host -- ONE copy per node in /dev/shm shared by the ranks
+# --------------------------------------------------------------------------------------------
+class HostBuffers:
+    def __init__(self, shared: bool, local: int, barrier, tag: str):
+        self.shared, self.local, self.barrier, self.tag = shared, local, barrier, tag
+        self.owners, self.paths, self.registered = [], [], []
+
+    def array(self, name: str, shape):
+        """Fortran-ordered float64 array in page-locked host memory."""
+        import torch
+        n = int(np.prod(shape))
+        if not self.shared:
+            t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            self.owners.append(t)
+            return t.numpy().reshape(shape, order="F")
+        path = f"/dev/shm/sisi4s_bench_{self.tag}_{name}"
+        if self.local == 0:
+            with open(path, "wb") as f:
+                f.truncate(n * 8)
+        self.barrier()
+        mm = np.memmap(path, dtype=np.float64, mode="r+", shape=(n,))
+        rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, n * 8, 0)
+        if int(rc) == 0:
+            self.registered.append(mm.ctypes.data)
+        self.owners.append(mm)
+        self.paths.append(path)
+        return mm.reshape(shape, order="F")
+
+    def close(self):
+        import torch
+        for p in self.registered:
+            torch.cuda.cudart().cudaHostUnregister(p)
+        self.owners.clear()
+        self.barrier()
+        if self.shared and self.local == 0:
+            for p in self.paths:
+                try:
+                    os.remove(p)
+                except OSError:
+                    pass
+
+
+def generate_inputs(wl, dev, host: HostBuffers, rank: int, world: int, seed: int = 2026):
+    """Synthetic inputs of sisi4s_b200.synthetic.make_inputs(kind="vertex"), with the large tensors
+    built on the GPU (torch FP64 einsum over the NF = 24 auxiliary index: setup plumbing, untimed) and
+    written straight into page-locked host memory, one hole slab at a time.  Every rank evaluates every
+    slab (so scalars derived from them are bitwise the same on all ranks) but, when the host copy is
+    shared, stores only its own share of the slabs."""
     import torch
-    t = torch.empty(arr.size, dtype=torch.float64, pin_memory=True)
-    out = t.numpy().reshape(arr.shape, order="F")
-    out[...] = arr
-    return out, t
+    from sisi4s_b200 import synthetic as S
+    o, v = wl["o"], wl["v"]
+    gamma = S.make_vertex(o, v, seed, NF_SYNTH)
+    epsi, epsa = S.eigenenergies(o, v)
+    np_ = o + v
+    a0 = np_ - v
+    parts = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (gamma.real, gamma.imag)]   # [F,p,q]
+    ei, ea = torch.from_numpy(epsi).to(dev), torch.from_numpy(epsa).to(dev)
+    want_pphh = wl["mode"] != "hole_block"          # config 5 rebuilds PPHH from the vertex per group
+    T2 = host.array("T2", (v, v, o, o))
+    Vpphh = host.array("Vpphh", (v, v, o, o)) if want_pphh else None
+    Vhhhp = host.array("Vhhhp", (o, o, o, v))
+    Vppph = host.array("Vppph", (v, v, v, o)) if wl["ppph_host"] else None
+    mine = (lambda j: True) if not host.shared else (lambda j: j % world == rank)
+
+    def contract(spec, ia, ib):
+        return sum(torch.einsum(spec, ia(g), ib(g)) for g in parts)
+
+    sq = torch.zeros((), dtype=torch.float64, device=dev)
+    ccsd = torch.zeros((), dtype=torch.float64, device=dev)
+    for j in range(o):
+        # Vabij[a,b,i,j] = G[G,a,i] G[G,b,j] (CoulombIntegralsFromVertex.cxx:402-403), as [i,b,a] = column-major [a,b,i]
+        vj = contract("Fai,Fb->iba", lambda g: g[:, a0:, :o], lambda g: g[:, a0:, j])
+        d2 = ei[:, None, None] + ei[j] - ea[None, :, None] - ea[None, None, :]
+        tj = vj / d2
+        sq += (tj * tj).sum()
+        ccsd += ((2.0 * vj - vj.transpose(1, 2)) * tj).sum()
+        if mine(j):
+            torch.from_numpy(T2[:, :, :, j].T).copy_(tj)
+            if want_pphh:
+                torch.from_numpy(Vpphh[:, :, :, j].T).copy_(vj)
+    # Vijka[i,j,k,a] = G[G,i,k] G[G,a,j] (:416-417), as [a,k,j,i]
+    if mine(0):
+        torch.from_numpy(Vhhhp.T).copy_(contract("Fik,Faj->akji", lambda g: g[:, :o, :o], lambda g: g[:, a0:, :o]))
+    if Vppph is not None:
+        for k in range(o):
+            if mine(k):
+                # Vabci[a,b,c,i] = G[G,a,c] G[G,b,i] (:430-431), as [c,b,a]
+                torch.from_numpy(Vppph[:, :, :, k].T).copy_(
+                    contract("Fac,Fb->cba", lambda g: g[:, a0:, a0:], lambda g: g[:, a0:, k]))
+    torch.cuda.synchronize(dev)
+    rms = float(torch.sqrt(sq / (float(v) * v * o * o)).item())
+    T1 = np.asfortranarray(S.normal(seed, 3, (v, o)) * rms)
+    host.barrier()
+    del parts
+    torch.cuda.empty_cache()
+    return S.TriplesInputs(o, v, epsi, epsa, T1, T2, Vpphh, Vhhhp, Vppph, gamma, float(ccsd.item()))
 
 
-def cpu_baseline_sample(inp, idx_pool, weights, budget_s=12.0, max_s=30.0):
-    """C restatement of the reference loop (oracle/pt_oracle.c) on all host cores, one sorted
-    triple at a time from idx_pool until the time budget is spent."""
+# --------------------------------------------------------------------------------------------
+# CPU side: the C restatement of the reference loop on sampled sorted triples of the workload
+# --------------------------------------------------------------------------------------------
+def oracle_triples(inp, idx):
+    """E_t of the sorted triples idx on the host cores (oracle/pt_oracle.c; dgemm through the OpenBLAS
+    that ships with scipy when that is the faster of the two).  The big integral tensors are handed
+    over lazily, so shapes whose PPPH / PPHH tensors are not on the host work too."""
     from oracle import c_oracle as CO
+    from sisi4s_b200 import synthetic as S
+    o, v = inp.o, inp.v
+    a0 = inp.Gamma.shape[1] - v
+    if inp.Vppph is not None and inp.Vpphh is not None:
+        return CO.triples_list(*inp.args(), np.asarray(idx))
+
+    def pphh_block(j, k):
+        if inp.Vpphh is not None:
+            return inp.Vpphh[:, :, j, k]
+        g = inp.Gamma
+        return (g.real[:, a0:, j].T @ g.real[:, a0:, k]) + (g.imag[:, a0:, j].T @ g.imag[:, a0:, k])
+
+    return CO.triples_list_blocks(inp.epsi, inp.epsa, inp.T1, inp.T2, pphh_block, inp.Vhhhp,
+                                  lambda z: S.ppph_slab_from_vertex(inp.Gamma, o, v, z), np.asarray(idx))
+
+
+def pick_cpu_gemm(inp, probe_idx):
+    """Time one sampled triple with the oracle's own blocked GEMM and with OpenBLAS; keep the faster."""
+    from oracle import c_oracle as CO
+    best = None
+    for blas in (False, True):
+        if blas and not CO.use_blas(True):
+            continue
+        if not blas:
+            CO.use_blas(False)
+        t0 = time.time()
+        oracle_triples(inp, [probe_idx])
+        dt = time.time() - t0
+        if best is None or dt < best[1]:
+            best = (blas, dt)
+    CO.use_blas(best[0])
+    return "OpenBLAS dgemm (scipy)" if best[0] else "oracle's blocked AVX2 GEMM"
+
+
+def cpu_sample(inp, pool, weights, budget_s=20.0, max_s=40.0):
+    """(energies, description dict) of sorted triples from `pool`, one at a time until the budget is spent."""
+    from oracle import c_oracle as CO
+    if 100 <= inp.v < 500:
+        gemm = pick_cpu_gemm(inp, pool[0])
+    elif inp.v >= 500 and CO.use_blas(True):       # one triple takes most of the budget: no probing
+        gemm = "OpenBLAS dgemm (scipy)"
+    else:
+        CO.use_blas(False)
+        gemm = "oracle's blocked AVX2 GEMM"
     t0 = time.time()
-    done, w = [], 0
-    for t in idx_pool:
-        CO.triples_list(*inp.args(), np.array([t]))
+    done, en, w = [], [], 0
+    for t in pool:
+        en.append(float(oracle_triples(inp, [t])[0]))
         done.append(int(t)); w += int(weights[t])
         el = time.time() - t0
         if el >= budget_s or el + el / len(done) > max_s:
             break
     el = time.time() - t0
-    return {"value": flops_of(inp.o, inp.v, w) / el * 1e-12, "unit": "TFLOP/s", "cores": CO.max_threads(),
-            "kind": "port", "seconds": el,
+    desc = {"value": flops_of(inp.o, inp.v, w) / el * 1e-12, "unit": "TFLOP/s", "cores": CO.max_threads(),
+            "kind": "port", "seconds": el, "cpu": CO.cpu_model(), "gemm": gemm,
             "sample": f"{len(done)} sorted triples {done} of the o={inp.o},v={inp.v} workload "
-                      f"({w} W blocks, {flops_of(inp.o, inp.v, w):.3e} FLOP)"}
+                      f"({w} W blocks, {flops_of(inp.o, inp.v, w):.3e} FLOP), incl. building the sampled PPPH slabs "
+                      "where the tensor is not on the host; C restatement of CcsdPerturbativeTriples.cxx:159-216 "
+                      "(sisi4s itself needs MPI + Cyclops CTF: unbuildable here)"}
+    return np.array(done), np.array(en), desc
 
 
-def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU algorithm for the path.  sisi4s itself (MPI +
-    Cyclops CTF) cannot be built here, so this times the C restatement of its loop
-    (oracle/pt_oracle.c, OpenMP over all host cores) on a bounded sample per step."""
+def run_reference_arm(args, wl, rank):
+    """--impl reference: the reference's CPU algorithm for the path.  sisi4s itself (MPI + Cyclops CTF)
+    cannot be built here, so this times the C restatement of its loop (oracle/pt_oracle.c, OpenMP +
+    BLAS over all host cores) on a bounded sample of sorted triples per step."""
     if rank != 0:
-        return
-    if not HOST_PPPH:
-        print(json.dumps({"impl": "reference", "unavailable": f"workload {args.workload}: the CPU arm needs the "
-                          "v^3 o PPPH tensor on the host; timed at o40v300 / o20v100 only"}), flush=True)
         return
     from oracle import c_oracle as CO
     from sisi4s_b200 import synthetic as S
-    inp = S.make_inputs(O_, V_, seed=2026, kind="vertex", nf=NF_SYNTH)
-    w = triple_weights(O_)
+    o, v = wl["o"], wl["v"]
+    if wl["mode"] == "hole_block" or not wl["ppph_host"]:
+        # host-generated inputs of these shapes take minutes of NumPy; the CPU arm of the large
+        # workloads is the `cpu_baseline` of the GPU arm's own line (same sampled triples)
+        print(json.dumps({"impl": "reference", "unavailable": f"workload {args.workload}: CPU arm reported as "
+                          "cpu_baseline of the GPU arm's line (sampled triples); standalone arm: o40v300 / o20v100"}), flush=True)
+        return
+    inp = S.make_inputs(o, v, seed=2026, kind="vertex", nf=NF_SYNTH)
+    w = triple_weights(o)
     ntr = w.size
-    per_step = 2  # sorted triples per step (bounded sample of that step's eighth)
+    nbatch = wl["nbatch"]
+    per_step = 2  # sorted triples per step (bounded sample of that step's share of the list)
     def step_triples(s):
-        b = (s % NBATCH) * ntr // NBATCH
-        return np.array([b + 17 + 3 * q for q in range(per_step)])
+        b = (s % nbatch) * ntr // nbatch
+        return [min(ntr - 1, b + 17 + 3 * q) for q in range(per_step)]
+    gemm = pick_cpu_gemm(inp, step_triples(0)[0]) if v >= 100 else "oracle's blocked AVX2 GEMM"
     for s in range(args.warmup):
-        CO.triples_list(*inp.args(), step_triples(s)[:1])
+        oracle_triples(inp, step_triples(s)[:1])
     t0 = time.time()
     fl = 0.0
     for s in range(args.steps):
         idx = step_triples(s)
-        CO.triples_list(*inp.args(), idx)
-        fl += flops_of(O_, V_, int(w[idx].sum()))
+        oracle_triples(inp, idx)
+        fl += flops_of(o, v, int(w[idx].sum()))
     el = time.time() - t0
     val = fl / el * 1e-12
     line = {
-        "impl": "reference", "metric": f"(T) FP64 TFLOP/s at o={O_},v={V_}", "value": val, "unit": "TFLOP/s",
+        "impl": "reference", "metric": f"(T) FP64 TFLOP/s at o={o},v={v}", "value": val, "unit": "TFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic UEG-style (T), o={O_} v={V_} (BASELINE {CONFIG_NAME})", "o": O_, "v": V_,
-                   "step": f"bounded sample: {per_step} sorted triples of the step's eighth of the triple list"},
+        "config": {"workload": f"synthetic UEG-style (T), o={o} v={v} (BASELINE {wl['config']})", "o": o, "v": v,
+                   "step": f"bounded sample: {per_step} sorted triples of the step's share of the triple list"},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": CO.max_threads(), "kind": "port",
+                         "cpu": CO.cpu_model(), "gemm": gemm,
                          "sample": f"{per_step} sorted triples per step, {args.steps} steps; C restatement of "
                                    "CcsdPerturbativeTriples.cxx:159-216 (sisi4s needs MPI+CTF, unbuildable here)"},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -213,23 +370,26 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="o40v300", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU oracle leg (parity + cpu_baseline)")
+    ap.add_argument("--e2e-share", type=int, default=0,
+                    help="e2e leg runs 1/SHARE of the sorted triples per rank-set (0 = workload default)")
     args = ap.parse_args()
-    global O_, V_, NBATCH, HOST_PPPH, CONFIG_NAME
-    O_, V_, NBATCH, HOST_PPPH, CONFIG_NAME = WORKLOADS[args.workload]
+    wl = WORKLOADS[args.workload]
+    o, v = wl["o"], wl["v"]
+    hole_block = wl["mode"] == "hole_block"
+    nbatch = wl.get("nbatch", 1)
     if args.steps is None:
-        args.steps = min(NBATCH, 8)
+        args.steps = {"o40v300": 8, "o20v100": 8, "o64v512": 8, "o100v800": 1}[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, wl, rank)
         return
 
     import torch
     import torch.distributed as dist
-    from sisi4s_b200 import synthetic as S
     from sisi4s_b200.triples import TriplesEngine, CcsdPerturbativeTriples
     from sisi4s_b200.sharding import TripleShards
 
@@ -258,77 +418,131 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    shards = TripleShards(O_, world, rank)
+    shards = TripleShards(o, world, rank)
 
     def allreduce(x, op):
         return shards.max(x, dev) if op is dist.ReduceOp.MAX else shards.sum(x, dev)
 
-    # ---- setup (untimed): inputs, FP64 ceiling, upload + pack
+    # ---- setup (untimed): inputs in page-locked host memory, FP64 ceiling, upload + pack
     t_setup = time.time()
-    inp = S.make_inputs(O_, V_, seed=2026, kind="vertex", nf=NF_SYNTH, with_ppph=HOST_PPPH)
-    # the large tensors live in page-locked host memory from here on (one copy per rank: the
-    # pageable originals are dropped, so that 8 ranks fit the host's memory)
-    keep = []
-    for field in ("T2", "Vpphh", "Vppph", "Vhhhp") if HOST_PPPH else ("T2", "Vpphh", "Vhhhp"):
-        view, owner = pinned_like(getattr(inp, field))
-        setattr(inp, field, view)
-        keep.append(owner)
-    weights = triple_weights(O_)
+    big = 8.0 * v * v * o * o * (1 if hole_block else 2) * world > 64e9   # N private copies would not be reasonable
+    host = HostBuffers(shared=(world > 1 and big), local=local, barrier=barrier,
+                       tag=f"{args.workload}_{os.environ.get('MASTER_PORT', '0')}")
+    inp = generate_inputs(wl, dev, host, rank, world)
+    weights = triple_weights(o)
+    tr_index = {t: n for n, t in enumerate(sorted_triples(o))} if hole_block else None
     peak_burst, peak_sust = measure_fp64_peak(dev)
-    eng = TriplesEngine(O_, V_, device=local)
-    eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph,
-                   vertex=None if HOST_PPPH else inp.Gamma)
+
+    def make_engine():
+        if hole_block:
+            en = TriplesEngine(o, v, device=local, hole_block=wl["block"])
+            en.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, None, None, vertex=inp.Gamma)
+        else:
+            en = TriplesEngine(o, v, device=local)
+            en.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph,
+                          vertex=None if wl["ppph_host"] else inp.Gamma)
+        return en
+
+    eng = make_engine()
     t_setup = time.time() - t_setup
 
-    def step_range(s):
-        return shards.my_range(NBATCH, s)
+    # ---- the steps
+    def group_triples(I, J, K):
+        b = wl["block"]
+        rng = lambda B: range(B * b, min(o, (B + 1) * b))
+        return [tr_index[(i, j, k)] for i in rng(I) for j in rng(J) for k in rng(K) if i <= j <= k]
+
+    def run_step(s, warm=False):
+        if not hole_block:
+            return eng.run(*shards.my_range(nbatch, s))
+        if warm:   # a diagonal group (56 sorted triples over 6 holes): warms the kernel and the clocks cheaply
+            return eng.run_list(group_triples(rank % 16, rank % 16, rank % 16))
+        # generic groups (I<J<K): rank r takes I = r, all ranks share J, K runs with the step
+        return eng.run_list(group_triples(rank % 8, 8, 9 + s % 7))
 
     for s in range(args.warmup):
-        eng.run(*step_range(s))
+        run_step(s, warm=True)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     dev_s = ker_s = fl = 0.0
     e_sum = 0.0
-    launches0 = eng.stats().kernel_launches
+    st0 = eng.stats()
     wall0 = time.time()
     for s in range(args.steps):
-        b, e = step_range(s)
-        res = eng.run(b, e)
+        res = run_step(s)
         dev_s += res.seconds; ker_s += res.seconds_kernel; fl += res.flops; e_sum += res.energy
     barrier()
     wall = time.time() - wall0
     clocks = sampler.stop() if rank == 0 else None
-    launches = eng.stats().kernel_launches - launches0
+    st1 = eng.stats()
+    launches = st1.kernel_launches - st0.kernel_launches
     t_max = allreduce(dev_s, dist.ReduceOp.MAX)
     k_max = allreduce(ker_s, dist.ReduceOp.MAX)
     fl_all = allreduce(fl, dist.ReduceOp.SUM)
     e_all = allreduce(e_sum, dist.ReduceOp.SUM)   # the one data collective
     launches_all = int(allreduce(float(launches), dist.ReduceOp.SUM))
     value = fl_all / t_max * 1e-12
+
+    # ---- parity + CPU baseline (rank 0 at N = 1): sampled sorted triples of this workload on the host cores
+    parity = cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if hole_block:
+            pool = [tr_index[t] for t in ((1, 50, 57), (3, 49, 49))]
+            budget = (1.0, 200.0)
+        elif v >= 500:
+            pool = [sorted_triples(o).index(t) for t in ((3, 17, 40), (5, 5, 30), (7, 21, 21))]
+            budget = (40.0, 120.0)
+        else:
+            pool = [int(t) for t in np.linspace(40, weights.size - 40, 48).astype(int)] if o >= 40 else \
+                   [int(t) for t in np.linspace(0, weights.size - 1, 24).astype(int)]
+            budget = (20.0, 40.0)
+        idx, e_cpu, cpu = cpu_sample(inp, pool, weights, *budget)
+        e_gpu = eng.run_list(idx).per_triple
+        diff = float(np.abs(e_gpu - e_cpu).max())
+        parity = {"triples": int(idx.size), "max_abs_diff": diff, "tol": TOL, "ok": bool(diff <= TOL),
+                  "checker": "oracle/pt_oracle.c on the same sorted triples of this workload",
+                  "max_abs_e_t": float(np.abs(e_cpu).max())}
+    # complete E(T) of the timed steps against the value recorded for this workload (N-independence)
+    golden_path = os.path.join(ROOT, "tests", "golden", "bench_energy.json")
+    full = (not hole_block) and args.steps % nbatch == 0
+    if rank == 0 and full and os.path.exists(golden_path):
+        want = json.load(open(golden_path)).get(args.workload)
+        if want is not None:
+            got = e_all / (args.steps // nbatch)
+            parity = dict(parity or {"tol": TOL, "ok": True})
+            parity.update(full_energy=got, full_energy_recorded=want, full_energy_diff=abs(got - want))
+            parity["ok"] = bool(parity["ok"] and abs(got - want) <= TOL)
     eng.close()
 
     # ---- end-to-end leg: plugin API, host (pinned) buffers -> energy
     e2e = None
-    if not args.no_e2e and NBATCH <= 8:   # larger workloads: one complete E(T) takes > 20 min on one GPU
-        big = dict(CcsdDoublesAmplitudes=inp.T2, PPHHCoulombIntegrals=inp.Vpphh,
-                   HHHPCoulombIntegrals=inp.Vhhhp)   # pinned (see setup)
-        if HOST_PPPH:
-            big["PPPHCoulombIntegrals"] = inp.Vppph
-        else:
-            big["CoulombVertex"] = inp.Gamma         # PPPH is built on the device
+    if not args.no_e2e:
         data = dict(HoleEigenEnergies=inp.epsi, ParticleEigenEnergies=inp.epsa, CcsdEnergy=inp.ccsd_energy,
-                    CcsdSinglesAmplitudes=inp.T1, **big)
+                    CcsdSinglesAmplitudes=inp.T1, CcsdDoublesAmplitudes=inp.T2)
+        if not hole_block:
+            data.update(PPHHCoulombIntegrals=inp.Vpphh, HHHPCoulombIntegrals=inp.Vhhhp)
+        if wl["ppph_host"]:
+            data["PPPHCoulombIntegrals"] = inp.Vppph
+        else:
+            data["CoulombVertex"] = inp.Gamma         # PPPH is built on the device
         argsmap = {k: "$" + k for k in data}
         argsmap["PerturbativeTriplesEnergy"] = "$PerturbativeTriplesEnergy"
         argsmap["device"] = local
+        if hole_block:
+            argsmap.update(holeBlock=wl["block"], integralsFromVertex=1)
+        # how much of E(T) the leg computes: everything, unless that takes > 10 min on these GPUs
+        share = args.e2e_share or (1 if hole_block else max(1, int(round(flops_of(o, v, o ** 3) / (world * 30e12 * 200.0)))))
 
         class Shard(CcsdPerturbativeTriples):
             """the plugin run() restricted to this rank's share of the sorted triples"""
             def run(self):
                 with self.make_engine() as en:
-                    r = en.run(*shards.my_range())
+                    if hole_block:
+                        r = en.run_list(group_triples(rank % 8, 8, 9))
+                    else:
+                        r = en.run(*shards.my_range(share, 0))
                     self.stats = en.stats()
                 return r
 
@@ -339,51 +553,65 @@ def main():
         e_e2e = allreduce(r.energy, dist.ReduceOp.SUM)
         barrier()
         w_e2e = allreduce(time.time() - w0, dist.ReduceOp.MAX)
-        fl_e2e = flops_of(O_, V_, int(weights.sum()))
+        fl_e2e = allreduce(r.flops, dist.ReduceOp.SUM)
+        what = ("one generic hole-block group per rank" if hole_block else
+                ("one complete E(T)" if share == 1 else f"1/{share} of the sorted triples"))
         e2e = {"value": fl_e2e / w_e2e * 1e-12, "unit": "TFLOP/s", "seconds": w_e2e,
                "h2d_bytes_per_step": float(alg.stats.bytes_h2d), "d2h_bytes_per_step": float(alg.stats.bytes_d2h),
-               "step": "one complete E(T): upload + pack + all sorted triples + energy read-back",
-               "energy": e_e2e + inp.ccsd_energy, "triples_energy": e_e2e}
+               "step": f"{what}: upload + pack + triples + energy read-back through the plugin API",
+               "energy": e_e2e + inp.ccsd_energy, "triples_energy": e_e2e,
+               "device_seconds_upload": float(alg.stats.seconds_upload), "device_seconds_run": float(alg.stats.seconds_run)}
+        if share == 1 and not hole_block and full and parity is not None and "full_energy" in parity:
+            parity["e2e_energy_diff"] = abs(e_e2e - parity["full_energy"])
+            parity["ok"] = bool(parity["ok"] and parity["e2e_energy_diff"] <= TOL)
 
-    cpu = None
-    if rank == 0 and world == 1 and HOST_PPPH and not args.no_cpu:   # reported at N=1 only
-        pool = [int(t) for t in np.linspace(40, weights.size - 40, 24).astype(int)]
-        cpu = cpu_baseline_sample(inp, pool, weights)
-
+    host.close()
     if rank == 0:
-        traffic = None
+        traffic = traffic_src = None
         prof = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
         if os.path.exists(prof) and args.workload == "o40v300":   # the capture is of this workload's step
             try:
-                # measured on one N=1 step (profiles/r01d_step_traffic.csv); a rank's launch covers 1/world of it
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch") / world
+                pj = json.load(open(prof))
+                # one ncu capture of an N=1 step; a rank's launch covers 1/world of it
+                traffic = pj.get("dram_bytes_per_launch") / world
+                traffic_src = pj.get("source")
             except Exception:
                 traffic = None
         achieved = fl_all / world / k_max * 1e-12   # per GPU: the roofline is the kernel's, not the job's
+        if hole_block:
+            step = (f"one generic hole-block group (block {wl['block']}: 216 sorted triples, 1296 W blocks) per rank and "
+                    f"step, staged from host T2 + rebuilt from the vertex inside the timed region; a "
+                    f"{fl_all / flops_of(o, v, o ** 3):.4f} sample of the complete E(T)")
+        else:
+            step = (f"1/{nbatch} of the sorted-triple list (weight-balanced contiguous chunk) per step, "
+                    f"split over {world} rank(s); {nbatch} steps = one complete E(T)")
         line = {
-            "metric": f"(T) FP64 TFLOP/s at o={O_},v={V_}", "value": value, "unit": "TFLOP/s", "n_gpus": world,
+            "metric": f"(T) FP64 TFLOP/s at o={o},v={v}", "value": value, "unit": "TFLOP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"synthetic UEG-style (T), o={O_} v={V_} (BASELINE {CONFIG_NAME})", "o": O_, "v": V_,
-                       "step": f"1/{NBATCH} of the sorted-triple list (weight-balanced contiguous chunk) per step, "
-                               f"split over {world} rank(s); {NBATCH} steps = one complete E(T)",
-                       "parallelism": f"triples sharded over {world} GPU(s), inputs replicated",
+            "config": {"workload": f"synthetic UEG-style (T), o={o} v={v} (BASELINE {wl['config']})", "o": o, "v": v,
+                       "step": step,
+                       "parallelism": f"triples sharded over {world} GPU(s), inputs "
+                                      + ("in host memory (one shared copy), staged per hole-block group" if hole_block else "replicated"),
                        "l2": "inputs (>= 0.2 GB/GPU packed; 11 GB at o=40,v=300) exceed the 126 MB L2; no flush needed",
                        "triples_energy_of_timed_steps": e_all, "wall_s_timed": wall,
-                       "wall_s_full_problem_est": t_max / args.steps * NBATCH, "setup_s": t_setup},
+                       "wall_s_full_problem_est": t_max / fl_all * flops_of(o, v, o ** 3), "setup_s": t_setup,
+                       "slab_loads": int(st1.slab_loads - st0.slab_loads), "groups_staged": int(st1.groups_staged - st0.groups_staged)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
-                         "frac": achieved / peak_burst, "traffic": traffic,
+                         "frac": achieved / peak_burst, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (burst; "
                                         f"sustained median {peak_sust:.2f}); MEASURED_PEAKS.json has no FP64 entry",
                          "frac_of_nominal_37": achieved / 37.0,
                          "kernel": "pt_fused_kernel", "algorithmic_flop": fl_all / world,
                          "per": "GPU (slowest rank's kernel time)"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
+            "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        sys.exit(1)
 
 
 if __name__ == "__main__":
