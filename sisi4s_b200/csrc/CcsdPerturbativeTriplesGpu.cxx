@@ -45,6 +45,22 @@ namespace {
   do {                                                                              \
     if ((call) != PT_OK) throw new EXCEPTION(std::string(#call ": ") + pt_last_error()); \
   } while (0)
+#define CUDA_CHECK(call)                                                                          \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) throw new EXCEPTION(std::string(#call ": ") + cudaGetErrorString(e_)); \
+  } while (0)
+#define NCCL_CHECK(call)                                                                          \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess) throw new EXCEPTION(std::string(#call ": ") + ncclGetErrorString(r_)); \
+  } while (0)
+
+// the library handle is released on every exit path, exceptions included
+struct PtGuard {
+  pt_handle_t h = nullptr;
+  ~PtGuard() { if (h) pt_destroy(h); }
+};
 
 // dense column-major copy of a CTF tensor; collective, executed by all ranks
 std::vector<double> gather(Tensor<double> *t) {
@@ -61,6 +77,41 @@ void expectShape(Tensor<double> *t, std::vector<int64_t> const &lens, std::strin
   if (!ok) throw new EXCEPTION("Incompatible shape of argument: " + name);
 }
 
+// sum of one double over all ranks.  One rank per GPU: a single ncclAllReduce over NVLink.  More
+// ranks than GPUs (ranks share devices, which one NCCL communicator does not allow): MPI.
+double allReduceEnergy(double local, CTF::World *world, int device, int deviceCount) {
+  const int rank(world->rank), np(world->np);
+  if (np == 1) return local;
+  double total(local);
+  if (np > deviceCount) {
+    if (MPI_Allreduce(&local, &total, 1, MPI_DOUBLE, MPI_SUM, world->comm) != MPI_SUCCESS)
+      throw new EXCEPTION("CcsdPerturbativeTriplesGpu: MPI_Allreduce failed");
+    return total;
+  }
+  ncclUniqueId id;
+  if (rank == 0) NCCL_CHECK(ncclGetUniqueId(&id));
+  if (MPI_Bcast(&id, sizeof(id), MPI_BYTE, 0, world->comm) != MPI_SUCCESS)
+    throw new EXCEPTION("CcsdPerturbativeTriplesGpu: MPI_Bcast of the NCCL id failed");
+  CUDA_CHECK(cudaSetDevice(device));
+  ncclComm_t comm;
+  NCCL_CHECK(ncclCommInitRank(&comm, np, id, rank));
+  double *dE(nullptr);
+  try {
+    CUDA_CHECK(cudaMalloc(&dE, sizeof(double)));
+    CUDA_CHECK(cudaMemcpy(dE, &local, sizeof(double), cudaMemcpyHostToDevice));
+    NCCL_CHECK(ncclAllReduce(dE, dE, 1, ncclDouble, ncclSum, comm, 0));
+    CUDA_CHECK(cudaStreamSynchronize(0));
+    CUDA_CHECK(cudaMemcpy(&total, dE, sizeof(double), cudaMemcpyDeviceToHost));
+  } catch (...) {
+    if (dE) cudaFree(dE);
+    ncclCommDestroy(comm);
+    throw;
+  }
+  cudaFree(dE);
+  ncclCommDestroy(comm);
+  return total;
+}
+
 } // namespace
 
 void CcsdPerturbativeTriplesGpu::run() {
@@ -70,20 +121,31 @@ void CcsdPerturbativeTriplesGpu::run() {
   const int Nv(epsa->lens[0]);
   CTF::World *world(epsi->wrld);
   const int rank(world->rank), np(world->np);
+  // mandatory, as in the reference (CcsdPerturbativeTriples.cxx:241, PerturbativeTriples.cxx:229)
+  const double eCcsd(getRealArgument("CcsdEnergy"));
 
-  // one rank <-> one GPU of the node (ranks beyond the GPU count share devices round-robin)
+  // one rank <-> one GPU of the node; with more ranks than GPUs the ranks share devices round-robin
+  // and the final reduction goes through MPI (allReduceEnergy)
   int deviceCount(0);
   if (cudaGetDeviceCount(&deviceCount) != cudaSuccess || deviceCount == 0)
     throw new EXCEPTION("CcsdPerturbativeTriplesGpu: no CUDA device (there is no CPU fallback)");
   const int device(getIntegerArgument("device", rank % deviceCount));
 
-  pt_handle_t h(nullptr);
-  PT_CHECK(pt_create(&h, No, Nv, device));
-  // optional: hole-blocked residency of V_abci for shapes whose v^3 o tensor exceeds the GPU's
-  // memory (slabSlots >= 3 slabs resident; the rest is rebuilt from the vertex / re-uploaded)
+  PtGuard guard;
+  PT_CHECK(pt_create(&guard.h, No, Nv, device));
+  pt_handle_t h(guard.h);
+  // Memory options for shapes that exceed one GPU (the reference's answer is sliceTensors + the
+  // per-triple vertex product, CcsdPerturbativeTriples.cxx:32-79,89-92):
+  //   holeBlock b : T2 / PPHH stay in host memory, triples are walked by hole-block groups of <= 3b
+  //                 active holes (BASELINE configs[4]: o=100, v=800);
+  //   slabSlots S : only V_abci is blocked (S >= 3 hole slabs resident).
+  const int64_t holeBlock(getIntegerArgument("holeBlock", 0));
   const int64_t slabSlots(getIntegerArgument("slabSlots", 0));
+  if (holeBlock > 0) PT_CHECK(pt_set_option(h, "hole_block", holeBlock));   // first: re-dimensions the buffers
   if (slabSlots > 0) PT_CHECK(pt_set_option(h, "slab_slots", slabSlots));
-  std::vector<double> hostPpph; // must outlive pt_run in the blocked PPPH contract
+  const bool blocked((holeBlock > 0) || (slabSlots > 0 && slabSlots < No));
+  // host copies the library reads on demand in the blocked modes: they must outlive pt_run
+  std::vector<double> hostT2, hostPphh, hostPpph;
 
   {
     std::vector<double> ei(gather(epsi)), ea(gather(epsa));
@@ -98,39 +160,45 @@ void CcsdPerturbativeTriplesGpu::run() {
   {
     Tensor<double> *Tabij(getTensorArgument("CcsdDoublesAmplitudes"));
     expectShape(Tabij, {Nv, Nv, No, No}, "CcsdDoublesAmplitudes");
-    std::vector<double> t2(gather(Tabij));
-    PT_CHECK(pt_set_doubles(h, t2.data()));
+    hostT2 = gather(Tabij);
+    PT_CHECK(pt_set_doubles(h, hostT2.data()));
+    if (holeBlock == 0) std::vector<double>().swap(hostT2);   // uploaded and packed: release the host copy
   }
-  {
+  const bool haveVertex(!isArgumentGiven("PPPHCoulombIntegrals"));
+  // integralsFromVertex: 1 -- build V_abij and V_ijka on the device from the vertex as well
+  // (CoulombIntegralsFromVertex.cxx:402-403,416-417), so neither has to be gathered from CTF
+  const bool integralsFromVertex(haveVertex && getIntegerArgument("integralsFromVertex", 0) != 0);
+  if (!integralsFromVertex) {
     Tensor<double> *Vabij(getTensorArgument("PPHHCoulombIntegrals"));
     expectShape(Vabij, {Nv, Nv, No, No}, "PPHHCoulombIntegrals");
-    std::vector<double> v(gather(Vabij));
-    PT_CHECK(pt_set_pphh(h, v.data()));
-  }
-  {
+    hostPphh = gather(Vabij);
+    PT_CHECK(pt_set_pphh(h, hostPphh.data()));
+    if (holeBlock == 0) std::vector<double>().swap(hostPphh);
     Tensor<double> *Vijka(getTensorArgument("HHHPCoulombIntegrals"));
     expectShape(Vijka, {No, No, No, Nv}, "HHHPCoulombIntegrals");
     std::vector<double> v(gather(Vijka));
     PT_CHECK(pt_set_hhhp(h, v.data()));
   }
-  if (isArgumentGiven("PPPHCoulombIntegrals")) {
-    // contract of PerturbativeTriples (PerturbativeTriples.cxx:176): one hole slab at a time,
-    // so that no rank ever holds more than v^3 doubles of V_abci on the host
+  if (!haveVertex) {
+    // contract of PerturbativeTriples (PerturbativeTriples.cxx:176)
     Tensor<double> *Vabci(getTensorArgument("PPPHCoulombIntegrals"));
     expectShape(Vabci, {Nv, Nv, Nv, No}, "PPPHCoulombIntegrals");
-    if (slabSlots > 0 && slabSlots < No) {
+    if (blocked) {
       hostPpph = gather(Vabci);
       PT_CHECK(pt_set_ppph_host(h, hostPpph.data()));
-    } else
-    for (int k(0); k < No; ++k) {
-      int start[] = {0, 0, 0, k}, end[] = {Nv, Nv, Nv, k + 1};
-      Tensor<double> slab(Vabci->slice(start, end));
-      std::vector<double> v(gather(&slab));
-      PT_CHECK(pt_set_ppph_slabs(h, k, k + 1, v.data()));
+    } else {
+      // one hole slab at a time, so that no rank ever holds more than v^3 doubles of V_abci on the host
+      for (int k(0); k < No; ++k) {
+        int start[] = {0, 0, 0, k}, end[] = {Nv, Nv, Nv, k + 1};
+        Tensor<double> slab(Vabci->slice(start, end));
+        std::vector<double> v(gather(&slab));
+        PT_CHECK(pt_set_ppph_slabs(h, k, k + 1, v.data()));
+      }
     }
   } else {
     // contract of the compiled CcsdPerturbativeTriples (:48-78): Coulomb vertex, Re/Im split;
-    // V_abci is then built on the device as CoulombIntegralsFromVertex.cxx:430-431
+    // V_abci is then built on the device as CoulombIntegralsFromVertex.cxx:430-431 -- all slabs at
+    // once, or (blocked modes) on demand from the resident vertex like the reference does (:89-92)
     Tensor<complex> *GammaFqr(getTensorArgument<complex>("CoulombVertex"));
     const int NF(GammaFqr->lens[0]), Np(GammaFqr->lens[1]);
     const int64_t n(static_cast<int64_t>(NF) * Np * Np);
@@ -142,6 +210,7 @@ void CcsdPerturbativeTriplesGpu::run() {
       im[q] = std::imag(g[q]);
     }
     PT_CHECK(pt_set_vertex(h, NF, Np, re.data(), im.data()));
+    if (integralsFromVertex) PT_CHECK(pt_use_vertex_integrals(h));
   }
 
   // this rank's share of the sorted triples (reference loop order, :156-158)
@@ -150,37 +219,20 @@ void CcsdPerturbativeTriplesGpu::run() {
   double eLocal(0.0);
   PT_CHECK(pt_run(h, begin, end, &eLocal, nullptr));
 
-  // the single collective of the path: all-reduce of the scalar energy over NVLink
-  double eTriples(eLocal);
-  if (np > 1) {
-    ncclUniqueId id;
-    if (rank == 0) ncclGetUniqueId(&id);
-    MPI_Bcast(&id, sizeof(id), MPI_BYTE, 0, world->comm);
-    ncclComm_t comm;
-    if (ncclCommInitRank(&comm, np, id, rank) != ncclSuccess)
-      throw new EXCEPTION("CcsdPerturbativeTriplesGpu: ncclCommInitRank failed");
-    double *dE(nullptr);
-    cudaSetDevice(device);
-    cudaMalloc(&dE, sizeof(double));
-    cudaMemcpy(dE, &eLocal, sizeof(double), cudaMemcpyHostToDevice);
-    ncclAllReduce(dE, dE, 1, ncclDouble, ncclSum, comm, 0);
-    cudaStreamSynchronize(0);
-    cudaMemcpy(&eTriples, dE, sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(dE);
-    ncclCommDestroy(comm);
-  }
-
   PtStats stats;
   PT_CHECK(pt_get_stats(h, &stats));
   PT_CHECK(pt_destroy(h));
+  guard.h = nullptr;
 
-  double eCcsd(getRealArgument("CcsdEnergy", 0.0));
+  // the single collective of the path: all-reduce of the scalar energy
+  const double eTriples(allReduceEnergy(eLocal, world, device, deviceCount));
+
   double e(eCcsd + eTriples);
   LOG(0, "CcsdPerturbativeTriplesGpu") << "e=" << e << std::endl;
   LOG(1, "CcsdPerturbativeTriplesGpu") << "ccsd=" << eCcsd << std::endl;
   LOG(1, "CcsdPerturbativeTriplesGpu") << "triples=" << eTriples << std::endl;
   LOG(1, "CcsdPerturbativeTriplesGpu")
-      << "device seconds=" << stats.seconds_run << ", TFLOP/s (rank 0 share)="
+      << "device seconds=" << stats.seconds_run << ", TFLOP/s (this rank's share)="
       << stats.flops_algorithmic / stats.seconds_run * 1e-12 << std::endl;
 
   // whichever spelling of the output the plan asks for
@@ -199,11 +251,9 @@ void CcsdPerturbativeTriplesGpu::run() {
 void CcsdPerturbativeTriplesGpu::dryRun() {
   DryTensor<> *epsi(getTensorArgument<double, DryTensor<double>>("HoleEigenEnergies"));
   DryTensor<> *epsa(getTensorArgument<double, DryTensor<double>>("ParticleEigenEnergies"));
-  const double No(epsi->lens[0]), Nv(epsa->lens[0]);
-  const double nr(std::ceil(Nv / 16.0));
-  // packed PPPH + two packed copies of T2 + PPHH and its pre-added pair sums + one staging slab,
-  // all FP64, per GPU
-  const double bytes(8.0 * (No * nr * nr * std::ceil(Nv / 4.0) * 1024.0 + 4.0 * Nv * Nv * No * No
-                            + Nv * Nv * Nv));
+  // the reference estimates its 8 live v^3 CTF tensors + sliced inputs (:250-284); this step lives in
+  // device memory, and the library knows what a handle of these dimensions will hold
+  const int64_t bytes(pt_estimate_device_bytes(epsi->lens[0], epsa->lens[0], getIntegerArgument("slabSlots", 0),
+                                               getIntegerArgument("holeBlock", 0)));
   LOG(0, "CcsdPerturbativeTriplesGpu") << "device memory per GPU=" << bytes / 1e9 << " GB" << std::endl;
 }

@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <string>
 #include <vector>
@@ -955,7 +957,19 @@ int pt_run_list(pt_handle_t h, int64_t n, const int64_t* triples, double* e_trip
   return run_triples(h, tr, e_triples, e_per_triple);
 }
 
+static double wall_now() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+#define PT_TRACE(tag)                                                                            \
+  do {                                                                                           \
+    if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[pt trace] %-18s %9.3f ms\n", tag, (wall_now() - t_trace) * 1e3); } \
+  } while (0)
+
 static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_triples, double* e_per_triple) {
+  const bool trace = getenv("PT_TRACE") != nullptr;
+  const double t_trace = wall_now();
   RC(sync_uploads(h));
   std::vector<double> e(tr.size(), 0.0);
   CU(cudaEventRecord(h->ev0, h->stream));
@@ -1036,6 +1050,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
       CU(h->grow(&h->d_e, &h->cap_e, list.size()));
       CU(h->grow(&h->d_item, &h->cap_item, max_items));
       CU(cudaMemcpyAsync(h->d_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+      PT_TRACE("lists ready");
       std::vector<cudaEvent_t> kev(2 * groups.size(), nullptr);
       struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (auto e : v) if (e) cudaEventDestroy(e); } } evguard{kev};
       for (auto& ev : kev) CU(cudaEventCreate(&ev));
@@ -1073,9 +1088,11 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
         CU(cudaEventRecord(kev[2 * gi], h->stream));
         CU(launch_fused(p, grid, h->stream));
         CU(cudaEventRecord(kev[2 * gi + 1], h->stream));
+        PT_TRACE("fused kernel done");
         CU(launch_reduce_items(h->d_item, p.ntriples, h->norbits, p.order, h->d_e + g.g0, h->stream));
         h->stats.kernel_launches += 2;
       }
+      PT_TRACE("reduce done");
       std::vector<double> el(list.size());
       CU(cudaMemcpyAsync(el.data(), h->d_e, list.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
@@ -1091,6 +1108,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
   }
   CU(cudaEventRecord(h->ev1, h->stream));
   CU(cudaEventSynchronize(h->ev1));
+  PT_TRACE("run done");
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->stats.seconds_run = ms * 1e-3;
