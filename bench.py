@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -166,8 +166,15 @@ class HostBuffers:
         self.barrier()
         mm = np.memmap(path, dtype=np.float64, mode="r+", shape=(n,))
         rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, n * 8, 0)
-        if int(rc) == 0:
+        try:
+            ok = int(rc) == 0
+        except (TypeError, ValueError):
+            ok = "success" in str(rc).lower()
+        if ok:
             self.registered.append(mm.ctypes.data)
+        else:
+            print(f"[bench] cudaHostRegister({name}) -> {rc}: copies from this buffer are staged by the driver",
+                  file=sys.stderr, flush=True)
         self.owners.append(mm)
         self.paths.append(path)
         return mm.reshape(shape, order="F")
@@ -473,6 +480,8 @@ def main():
     for s in range(args.steps):
         res = run_step(s)
         dev_s += res.seconds; ker_s += res.seconds_kernel; fl += res.flops; e_sum += res.energy
+        if rank == 0:
+            print(f"[bench] step {s}: device {res.seconds:.4f} s, kernel {res.seconds_kernel:.4f} s", file=sys.stderr, flush=True)
     barrier()
     wall = time.time() - wall0
     clocks = sampler.stop() if rank == 0 else None
