@@ -152,29 +152,33 @@ class HostBuffers:
         self.owners, self.paths, self.registered = [], [], []
 
     def array(self, name: str, shape):
-        """Fortran-ordered float64 array in page-locked host memory."""
+        """Fortran-ordered float64 array in host memory: page-locked when private; a shared /dev/shm
+        mapping is left pageable here (the library page-locks it read-only itself: option pin_host)."""
         import torch
         n = int(np.prod(shape))
         if not self.shared:
-            t = torch.empty(n, dtype=torch.float64, pin_memory=True)
-            self.owners.append(t)
-            return t.numpy().reshape(shape, order="F")
+            # numpy memory + cudaHostRegister: exact size (torch's pinned allocator rounds up to 2^k bytes)
+            a = np.empty(n, dtype=np.float64)
+            rc = torch.cuda.cudart().cudaHostRegister(a.ctypes.data, n * 8, 0)
+            try:
+                ok = int(rc) == 0
+            except (TypeError, ValueError):
+                ok = "success" in str(rc).lower()
+            if ok:
+                self.registered.append(a.ctypes.data)
+                self.owners.append(a)
+            else:
+                del a
+                t = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                self.owners.append(t)
+                a = t.numpy()
+            return a.reshape(shape, order="F")
         path = f"/dev/shm/sisi4s_bench_{self.tag}_{name}"
         if self.local == 0:
             with open(path, "wb") as f:
                 f.truncate(n * 8)
         self.barrier()
         mm = np.memmap(path, dtype=np.float64, mode="r+", shape=(n,))
-        rc = torch.cuda.cudart().cudaHostRegister(mm.ctypes.data, n * 8, 0)
-        try:
-            ok = int(rc) == 0
-        except (TypeError, ValueError):
-            ok = "success" in str(rc).lower()
-        if ok:
-            self.registered.append(mm.ctypes.data)
-        else:
-            print(f"[bench] cudaHostRegister({name}) -> {rc}: copies from this buffer are staged by the driver",
-                  file=sys.stderr, flush=True)
         self.owners.append(mm)
         self.paths.append(path)
         return mm.reshape(shape, order="F")
@@ -432,7 +436,11 @@ def main():
 
     # ---- setup (untimed): inputs in page-locked host memory, FP64 ceiling, upload + pack
     t_setup = time.time()
-    big = 8.0 * v * v * o * o * (1 if hole_block else 2) * world > 64e9   # N private copies would not be reasonable
+    # N private page-locked copies of the large tensors, unless they would take more than 40 % of the host's
+    # memory: then ONE copy per node in /dev/shm, shared by the ranks
+    import psutil
+    need = 8.0 * v * v * o * o * (1 if hole_block else 2) * world + (8.0 * v ** 3 * o * world if wl["ppph_host"] else 0.0)
+    big = need > 0.4 * psutil.virtual_memory().total or os.environ.get("BENCH_SHARED_HOST") == "1"
     host = HostBuffers(shared=(world > 1 and big), local=local, barrier=barrier,
                        tag=f"{args.workload}_{os.environ.get('MASTER_PORT', '0')}")
     inp = generate_inputs(wl, dev, host, rank, world)
@@ -442,7 +450,7 @@ def main():
 
     def make_engine():
         if hole_block:
-            en = TriplesEngine(o, v, device=local, hole_block=wl["block"])
+            en = TriplesEngine(o, v, device=local, hole_block=wl["block"], pin_host=host.shared)
             en.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, None, None, vertex=inp.Gamma)
         else:
             en = TriplesEngine(o, v, device=local)
@@ -540,7 +548,7 @@ def main():
         argsmap["PerturbativeTriplesEnergy"] = "$PerturbativeTriplesEnergy"
         argsmap["device"] = local
         if hole_block:
-            argsmap.update(holeBlock=wl["block"], integralsFromVertex=1)
+            argsmap.update(holeBlock=wl["block"], integralsFromVertex=1, pinHost=int(host.shared))
         # how much of E(T) the leg computes: everything, unless that takes > 10 min on these GPUs
         share = args.e2e_share or (1 if hole_block else max(1, int(round(flops_of(o, v, o ** 3) / (world * 30e12 * 200.0)))))
 
@@ -568,8 +576,10 @@ def main():
         e2e = {"value": fl_e2e / w_e2e * 1e-12, "unit": "TFLOP/s", "seconds": w_e2e,
                "h2d_bytes_per_step": float(alg.stats.bytes_h2d), "d2h_bytes_per_step": float(alg.stats.bytes_d2h),
                "step": f"{what}: upload + pack + triples + energy read-back through the plugin API",
+               "host_buffers": "one /dev/shm copy per node shared by the ranks" + (", page-locked read-only by the library" if hole_block else " (pageable)") if host.shared else "page-locked, private per rank",
                "energy": e_e2e + inp.ccsd_energy, "triples_energy": e_e2e,
-               "device_seconds_upload": float(alg.stats.seconds_upload), "device_seconds_run": float(alg.stats.seconds_run)}
+               "device_seconds_upload": float(alg.stats.seconds_upload), "device_seconds_run": float(alg.stats.seconds_run),
+               "bytes_page_locked_by_library": float(alg.stats.bytes_pinned)}
         if share == 1 and not hole_block and full and parity is not None and "full_energy" in parity:
             parity["e2e_energy_diff"] = abs(e_e2e - parity["full_energy"])
             parity["ok"] = bool(parity["ok"] and parity["e2e_energy_diff"] <= TOL)

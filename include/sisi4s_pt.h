@@ -62,6 +62,7 @@ typedef struct PtStats {
   int32_t reserved;
   int64_t slab_loads;        /* PPPH slabs (re)built or re-uploaded on demand (slab_slots < o) */
   int64_t groups_staged;     /* hole-block groups whose T2 / PPHH / HHHP blocks were staged (hole_block)  */
+  double bytes_pinned;       /* caller-owned host memory page-locked by the library (pin_host)            */
 } PtStats;
 
 /* ---- lifecycle ---------------------------------------------------------- */

@@ -31,6 +31,7 @@ class PtStats(C.Structure):
         ("reserved", C.c_int32),
         ("slab_loads", C.c_int64),
         ("groups_staged", C.c_int64),
+        ("bytes_pinned", C.c_double),
     ]
 
 

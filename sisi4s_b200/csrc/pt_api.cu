@@ -198,12 +198,28 @@ int upload(pt_handle_t h, double* dst, const double* src, size_t n) {
   return PT_OK;
 }
 
+// page-lock a caller-owned tensor for full-speed DMA (option pin_host).  Read-only registration first:
+// it is the one the kernel grants for shared file mappings (/dev/shm).  In 1 GiB pieces, all or
+// nothing -- a half-locked buffer would make copies that straddle the boundary fail; when the memory
+// is already page-locked by the caller, or cannot be locked, the copies simply stay as they are.
 void pin(pt_handle_t h, const double* p, size_t n) {
   if (!h->pin_host || !p) return;
-  cudaError_t e = cudaHostRegister((void*)p, n * sizeof(double), cudaHostRegisterReadOnly);
-  if (e == cudaErrorNotSupported) { cudaGetLastError(); e = cudaHostRegister((void*)p, n * sizeof(double), cudaHostRegisterDefault); }
-  if (e == cudaSuccess) h->registered.push_back((void*)p);
-  else cudaGetLastError();   // already pinned by the caller, or not lockable: the copies still work
+  const size_t bytes = n * sizeof(double), piece = (size_t)1 << 30;
+  std::vector<void*> done;
+  for (size_t off = 0; off < bytes; off += piece) {
+    void* q = (char*)p + off;
+    const size_t len = std::min(piece, bytes - off);
+    cudaError_t e = cudaHostRegister(q, len, cudaHostRegisterReadOnly);
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaHostRegister(q, len, cudaHostRegisterDefault); }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (void* r : done) cudaHostUnregister(r);
+      return;
+    }
+    done.push_back(q);
+  }
+  h->registered.insert(h->registered.end(), done.begin(), done.end());
+  h->stats.bytes_pinned += (double)bytes;
 }
 
 int configure_kernels() {
@@ -964,11 +980,11 @@ static double wall_now() {
 }
 #define PT_TRACE(tag)                                                                            \
   do {                                                                                           \
-    if (trace) { cudaStreamSynchronize(h->stream); fprintf(stderr, "[pt trace] %-18s %9.3f ms\n", tag, (wall_now() - t_trace) * 1e3); } \
+    if (trace) { if (trace == 1) cudaStreamSynchronize(h->stream); fprintf(stderr, "[pt trace] %-18s %9.3f ms\n", tag, (wall_now() - t_trace) * 1e3); } \
   } while (0)
 
 static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_triples, double* e_per_triple) {
-  const bool trace = getenv("PT_TRACE") != nullptr;
+  const int trace = getenv("PT_TRACE") ? atoi(getenv("PT_TRACE")) : 0;   // 1: marks after a stream sync, 2: host-side marks only
   const double t_trace = wall_now();
   RC(sync_uploads(h));
   std::vector<double> e(tr.size(), 0.0);
@@ -1046,9 +1062,14 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
         groups.push_back(std::move(g));
         g0 = g1;
       }
-      CU(h->grow(&h->d_list, &h->cap_list, list.size()));
-      CU(h->grow(&h->d_e, &h->cap_e, list.size()));
-      CU(h->grow(&h->d_item, &h->cap_item, max_items));
+      PT_TRACE("host lists built");
+      // grow-only scratch with headroom: the partitions of one problem differ by a few per cent in their
+      // number of triples, and a reallocation in the middle of a run costs a device synchronisation
+      const size_t room_l = list.size() + list.size() / 4 + 64, room_i = max_items + max_items / 4 + 64;
+      if (list.size() > h->cap_list) CU(h->grow(&h->d_list, &h->cap_list, room_l));
+      if (list.size() > h->cap_e) CU(h->grow(&h->d_e, &h->cap_e, room_l));
+      if (max_items > h->cap_item) CU(h->grow(&h->d_item, &h->cap_item, room_i));
+      PT_TRACE("scratch ready");
       CU(cudaMemcpyAsync(h->d_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
       PT_TRACE("lists ready");
       std::vector<cudaEvent_t> kev(2 * groups.size(), nullptr);
@@ -1086,7 +1107,9 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
           p.sync_every = h->item_sync;
         }
         CU(cudaEventRecord(kev[2 * gi], h->stream));
+        PT_TRACE("before launch");
         CU(launch_fused(p, grid, h->stream));
+        PT_TRACE("launched");
         CU(cudaEventRecord(kev[2 * gi + 1], h->stream));
         PT_TRACE("fused kernel done");
         CU(launch_reduce_items(h->d_item, p.ntriples, h->norbits, p.order, h->d_e + g.g0, h->stream));

@@ -383,7 +383,8 @@ class CcsdPerturbativeTriples(Algorithm):
                             keep_raw=(engine == _lib.PT_ENGINE_NAIVE),
                             slab_slots=self.getIntegerArgument("slabSlots", 0),
                             hole_block=self.getIntegerArgument("holeBlock", 0),
-                            async_upload=bool(self.getIntegerArgument("asyncUpload", 1)))
+                            async_upload=bool(self.getIntegerArgument("asyncUpload", 1)),
+                            pin_host=bool(self.getIntegerArgument("pinHost", 0)))
         eng.set_eigenenergies(epsi, epsa)
         eng.set_singles(self.getTensorArgument("CcsdSinglesAmplitudes"))
         eng.set_doubles(self.getTensorArgument("CcsdDoublesAmplitudes"))
