@@ -198,27 +198,17 @@ int upload(pt_handle_t h, double* dst, const double* src, size_t n) {
   return PT_OK;
 }
 
-// page-lock a caller-owned tensor for full-speed DMA (option pin_host).  Read-only registration first:
-// it is the one the kernel grants for shared file mappings (/dev/shm).  In 1 GiB pieces, all or
-// nothing -- a half-locked buffer would make copies that straddle the boundary fail; when the memory
-// is already page-locked by the caller, or cannot be locked, the copies simply stay as they are.
+// page-lock a caller-owned tensor for full-speed DMA (option pin_host), as ONE region (a copy must not
+// straddle two registrations).  Read-only registration first: it is the one the kernel grants for
+// shared file mappings (/dev/shm).  When the memory is already page-locked by the caller, or cannot
+// be locked, the copies simply stay as they are (staged by the driver).
 void pin(pt_handle_t h, const double* p, size_t n) {
   if (!h->pin_host || !p) return;
-  const size_t bytes = n * sizeof(double), piece = (size_t)1 << 30;
-  std::vector<void*> done;
-  for (size_t off = 0; off < bytes; off += piece) {
-    void* q = (char*)p + off;
-    const size_t len = std::min(piece, bytes - off);
-    cudaError_t e = cudaHostRegister(q, len, cudaHostRegisterReadOnly);
-    if (e != cudaSuccess) { cudaGetLastError(); e = cudaHostRegister(q, len, cudaHostRegisterDefault); }
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      for (void* r : done) cudaHostUnregister(r);
-      return;
-    }
-    done.push_back(q);
-  }
-  h->registered.insert(h->registered.end(), done.begin(), done.end());
+  const size_t bytes = n * sizeof(double);
+  cudaError_t e = cudaHostRegister((void*)p, bytes, cudaHostRegisterReadOnly);
+  if (e != cudaSuccess) { cudaGetLastError(); e = cudaHostRegister((void*)p, bytes, cudaHostRegisterDefault); }
+  if (e != cudaSuccess) { cudaGetLastError(); return; }
+  h->registered.push_back((void*)p);
   h->stats.bytes_pinned += (double)bytes;
 }
 
