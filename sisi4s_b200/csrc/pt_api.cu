@@ -263,6 +263,7 @@ VgParams vg_base(pt_handle_t h) {
   p.nr = h->d.nr;
   p.nk4 = h->d.nk4;
   p.nb0 = p.nb1 = 1;
+  p.alpha = 1.0;
   return p;
 }
 // Vabci["abci"] = G["Gac"] G["Gbi"] (:430-431): slab z, kernel naming V[b,c,d,z] = sum_G G[G,b,d] G[G,c,z],

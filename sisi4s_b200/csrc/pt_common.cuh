@@ -130,8 +130,12 @@ cudaError_t launch_reduce_items(const double* e_item, int ntriples, int norbits,
 // ---- integrals from the vertex (pt_pack.cu): one K-major image of the vertex, batched DMMA GEMMs
 enum { VG_STRIDED = 0, VG_PACKED = 1 };
 struct VgParams {
-  const double* gp;        // Gp[kc][r][4], r = p + np q
+  const double* gp;        // Gp[kc][r][4], r = p + np q   (A operand; also the B operand unless gpb is set)
   long long rows_padded;
+  const double* gpb;       // optional separate K-major image of the B operand (tensor engine), rows_padded_b rows
+  long long rows_padded_b;
+  double alpha, beta;      // VG_STRIDED: out = alpha * acc (+ beta * out when accumulate)
+  int accumulate;
   int kp4;                 // K chunks of 4 (K = 2 nf padded to a multiple of 16)
   int mode;
   // VG_STRIDED: batch (b0, b1) -> first rows / output offset; optional index maps (hole subsets)

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
     const long long row = isA ? rowA : rowB;
     const uint32_t bytes = isA ? 512u : 4096u;
     const uint32_t soff = isA ? (uint32_t)((kcl * VG_BM + 16 * (lane & 3)) * 32) : (uint32_t)(VG_BM * 128 + kcl * VG_BN * 32);
-    const double* src = p.gp + (size_t)row * 4;
+    const double* src = ((isA || !p.gpb) ? p.gp : p.gpb) + (size_t)row * 4;
+    const size_t kstride = (size_t)((isA || !p.gpb) ? p.rows_padded : p.rows_padded_b) * 4;   // doubles per K chunk of 4
     for (int s = 0; s < nstage; ++s) {
       const int slot = s % VG_STAGES;
       const uint32_t ph = (uint32_t)(s / VG_STAGES) & 1u;
@@ -288,8 +289,7 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
       if (lane == 0) vg_mbar_expect_tx(full_u + 8 * slot, (uint32_t)(VG_STAGE_DBL * 8));
       __syncwarp();
       if (act)
-        vg_bulk_g2s(ring_u + slot * (VG_STAGE_DBL * 8) + soff, src + (size_t)(4 * s + kcl) * (size_t)p.rows_padded * 4,
-                    bytes, full_u + 8 * slot);
+        vg_bulk_g2s(ring_u + slot * (VG_STAGE_DBL * 8) + soff, src + (size_t)(4 * s + kcl) * kstride, bytes, full_u + 8 * slot);
     }
     return;
   }
@@ -352,7 +352,10 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int n = VG_BN * nt + 32 * wn + 8 * j + t2 + e;
-          if (n < p.N) p.out[outoff + (long long)m * p.sm + (long long)n * p.sn] = acc[i][j][e];
+          if (n < p.N) {
+            double* o = p.out + outoff + (long long)m * p.sm + (long long)n * p.sn;
+            *o = p.accumulate ? p.alpha * acc[i][j][e] + p.beta * *o : p.alpha * acc[i][j][e];
+          }
         }
     }
   }

@@ -129,11 +129,12 @@ class UegVertexGenerator(Algorithm):
 
 @register
 class CoulombIntegralsFromVertex(Algorithm):
-    """Real Coulomb integral blocks from the vertex, reference src/algorithms/
+    """Real Coulomb integral blocks from the vertex ON THE DEVICE, reference src/algorithms/
     CoulombIntegralsFromVertex.cxx:390-433 (directly computed blocks, V = Re.Re + Im.Im with the
-    reference's index strings) and :436-560 (blocks derived by index permutation).  Host-side
-    (NumPy); `complex: 1` and `antisymmetrize: 1` are not supported.  Only the blocks named in the
-    step's `out:` map are built."""
+    reference's index strings) and :436-560 (blocks derived by index permutation).  Every statement is
+    one contraction / permuted copy of the device tensor engine (tensor_engine.DeviceTensors: the
+    library's FP64 tensor-core GEMM).  `complex: 1` and `antisymmetrize: 1` are not supported.  Only the
+    blocks named in the step's `out:` map are built."""
     name = "CoulombIntegralsFromVertex"
     # name -> (first vertex part, its indices, second part, its indices, output indices)
     DIRECT = {"PPHHCoulombIntegrals": ("ai", "ai", "ai", "bj", "abij"),      # :402-403
@@ -154,13 +155,8 @@ class CoulombIntegralsFromVertex(Algorithm):
                "PHHHCoulombIntegrals": ("HHHPCoulombIntegrals", "kjia", "aijk"),   # :539
                "HPHHCoulombIntegrals": ("HHHPCoulombIntegrals", "jkia", "iajk")}   # :551
 
-    def _direct(self, name, parts):
-        p1, i1, p2, i2, out = self.DIRECT[name]
-        a, b = parts[p1], parts[p2]
-        return np.asfortranarray(np.einsum(f"G{i1},G{i2}->{out}", a.real, b.real, optimize=True)
-                                 + np.einsum(f"G{i1},G{i2}->{out}", a.imag, b.imag, optimize=True))
-
     def run(self):
+        from .tensor_engine import DeviceTensors
         if self.getIntegerArgument("complex", 0) or self.getIntegerArgument("antisymmetrize", 0):
             raise SisiException("CoulombIntegralsFromVertex: only real, non-antisymmetrized integrals")
         g = self.getTensorArgument("CoulombVertex")
@@ -168,50 +164,83 @@ class CoulombIntegralsFromVertex(Algorithm):
         nv = int(self.getTensorArgument("ParticleEigenEnergies").shape[0])
         np_ = g.shape[1]
         h, pt = slice(0, no), slice(np_ - nv, np_)                       # particles = last Nv states (:121-136)
-        parts = {"ij": g[:, h, h], "ai": g[:, pt, h], "ab": g[:, pt, pt]}
-        cache = {}
-        for name in list(self.DIRECT) + list(self.DERIVED):
-            if not self.isArgumentGiven(name):
-                continue
-            if name in self.DIRECT:
-                cache.setdefault(name, self._direct(name, parts))
-                val = cache[name]
-            else:
-                src, si, so = self.DERIVED[name]
-                cache.setdefault(src, self._direct(src, parts))
-                val = np.asfortranarray(np.einsum(f"{si}->{so}", cache[src]))
-            self.data[_data_name(self, name)] = val
+        extent = lambda letters: tuple(nv if c in "abcd" else no for c in letters)
+        wanted = [n for n in list(self.DIRECT) + list(self.DERIVED) if self.isArgumentGiven(n)]
+        with DeviceTensors(self.getIntegerArgument("device", 0)) as eng:
+            parts = {}
+            for key, blk in (("ij", g[:, h, h]), ("ai", g[:, pt, h]), ("ab", g[:, pt, pt])):
+                parts[key] = (eng.tensor(blk.shape, blk.real), eng.tensor(blk.shape, blk.imag))   # fromComplexTensor
+            cache = {}
+
+            def direct(name):
+                if name not in cache:
+                    p1, i1, p2, i2, out = self.DIRECT[name]
+                    t = eng.tensor(extent(out))
+                    for part, beta in ((0, 0.0), (1, 1.0)):              # Re.Re, then += Im.Im
+                        eng.contract(1.0, parts[p1][part], "G" + i1, parts[p2][part], "G" + i2, beta, t, out)
+                    cache[name] = t
+                return cache[name]
+
+            for name in wanted:
+                if name in self.DIRECT:
+                    val = direct(name).get()
+                else:
+                    src, si, so = self.DERIVED[name]
+                    t = eng.tensor(extent(so))
+                    eng.add(1.0, direct(src), si, 0.0, t, so)
+                    val = t.get()
+                    t.free()
+                self.data[_data_name(self, name)] = val
 
 
 @register
 class CcsdEnergyFromCoulombIntegralsReference(Algorithm):
-    """CCSD step in front of the triples (reference CcsdEnergyFromCoulombIntegralsReference.cxx /
-    ClusterSinglesDoublesAlgorithm.cxx:37-128; outputs CcsdEnergy, CcsdSinglesAmplitudes,
-    CcsdDoublesAmplitudes).  Solved by sisi4s_b200/ccsd.py from the CoulombVertex (library GEMMs on the
-    GPU), so the step needs `CoulombVertex` in its `in:` map; the integral-block arguments of the
-    reference's plans are accepted and ignored.  Runs on `device` (default cuda:0; `device: cpu` must be
-    asked for explicitly)."""
+    """CCSD step in front of the triples: reference CcsdEnergyFromCoulombIntegralsReference.cxx:29-295
+    driven by ClusterSinglesDoublesAlgorithm.cxx:37-128, on the device (sisi4s_b200/ccsd.py).  Same
+    arguments as the reference: the integral blocks PPHH, PHPH, HHHH, HHHP, PPPH, PPPP, eigenenergies,
+    `mixer` (LinearMixer default / DiisMixer), `maxResidua`, `mixingRatio`, `maxIterations`,
+    `energyConvergence`, `amplitudesConvergence` (relative criteria), `levelShift`; outputs CcsdEnergy,
+    CcsdSinglesAmplitudes, CcsdDoublesAmplitudes.  Blocks that are missing are built from `CoulombVertex`
+    when the plan passes it.  Not converging is a logged WARNING, as in the reference (:120-124)."""
     name = "CcsdEnergyFromCoulombIntegralsReference"
 
     def run(self):
-        import torch
         from . import ccsd
-        if not self.isArgumentGiven("CoulombVertex"):
-            raise SisiException("Missing argument: CoulombVertex")
-        device = _text(self, "device", "cuda:0")
-        if device.startswith("cuda") and not torch.cuda.is_available():
-            raise SisiException("CcsdEnergyFromCoulombIntegralsReference: no CUDA device (pass `device: cpu` to run on the host)")
+        epsi = self.getTensorArgument("HoleEigenEnergies")
+        epsa = self.getTensorArgument("ParticleEigenEnergies")
+        V, missing = {}, []
+        for b in ccsd.BLOCKS:
+            key = b + "CoulombIntegrals"
+            if self.isArgumentGiven(key):
+                V[b] = self.getTensorArgument(key)
+            else:
+                missing.append(key)
+        if missing:
+            if not self.isArgumentGiven("CoulombVertex"):
+                raise SisiException(f"Missing argument: {missing[0]}")
+            sub = {"CoulombVertex": self.arguments["CoulombVertex"], "HoleEigenEnergies": self.arguments["HoleEigenEnergies"],
+                   "ParticleEigenEnergies": self.arguments["ParticleEigenEnergies"]}
+            tmp = dict(self.data)
+            sub.update({k: "$" + k for k in missing})
+            CoulombIntegralsFromVertex(sub, tmp).run()
+            for k in missing:
+                V[k[:4]] = tmp[k]
         out = []
-        res = ccsd.solve_ccsd(self.getTensorArgument("HoleEigenEnergies"), self.getTensorArgument("ParticleEigenEnergies"),
-                              self.getTensorArgument("CoulombVertex"), device,
-                              energy_convergence=self.getRealArgument("energyConvergence", 1e-6),
-                              amplitudes_convergence=self.getRealArgument("amplitudesConvergence", 1e-5),
-                              max_iterations=self.getIntegerArgument("maxIterations", 16),
-                              max_residua=self.getIntegerArgument("maxResidua", 4), log=out.append)
+        mixer = _text(self, "mixer", "LinearMixer")
+        if mixer not in ("LinearMixer", "DiisMixer"):
+            raise SisiException(f"Mixer not implemented: {mixer}")        # ClusterSinglesDoublesAlgorithm.cxx:50-54
+        res = ccsd.solve_ccsd(epsi, epsa, V, device=self.getIntegerArgument("device", 0), mixer=mixer,
+                              max_residua=self.getIntegerArgument("maxResidua", 4),
+                              mixing_ratio=self.getRealArgument("mixingRatio", 1.0),
+                              max_iterations=self.getIntegerArgument("maxIterations", ccsd.DEFAULT_MAX_ITERATIONS),
+                              energy_convergence=self.getRealArgument("energyConvergence", ccsd.DEFAULT_ENERGY_CONVERGENCE),
+                              amplitudes_convergence=self.getRealArgument("amplitudesConvergence", ccsd.DEFAULT_AMPLITUDES_CONVERGENCE),
+                              level_shift=self.getRealArgument("levelShift", ccsd.DEFAULT_LEVEL_SHIFT), log=out.append)
         self.log = {"e": res["energy"]}
         self.iterations = out
+        self.converged = res["converged"]
         if not res["converged"]:
-            raise SisiException(f"CCSD did not converge in {res['iterations']} iterations")
+            self.note = "WARNING: energy or amplitudes convergence not reached."
         self.setRealArgument("CcsdEnergy", res["energy"])
         for key, val in (("CcsdSinglesAmplitudes", res["T1"]), ("CcsdDoublesAmplitudes", res["T2"])):
             if self.isArgumentGiven(key):
@@ -220,7 +249,7 @@ class CcsdEnergyFromCoulombIntegralsReference(Algorithm):
 
 @register
 class CcsdEnergyFromCoulombIntegrals(CcsdEnergyFromCoulombIntegralsReference):
-    """Same step under the reference's other name (takes the CoulombVertex in the reference, too)."""
+    """Same step under the reference's other name."""
     name = "CcsdEnergyFromCoulombIntegrals"
 
 
