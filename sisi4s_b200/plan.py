@@ -105,6 +105,27 @@ class DefineHolesAndParticles(Algorithm):
 
 
 @register
+class CoulombVertexReader(Algorithm):
+    """Legacy FTODDUMP reader (reference src/algorithms/CoulombVertexReader.cxx:27-108): `file` ->
+    HoleEigenEnergies, ParticleEigenEnergies, CoulombVertex.  `unrestricted: 1` (:172-180) is not
+    supported (the (T) step here is closed shell)."""
+    name = "CoulombVertexReader"
+
+    def run(self):
+        if self.getIntegerArgument("unrestricted", 0):
+            raise SisiException("CoulombVertexReader: unrestricted vertices are not supported")
+        try:
+            epsi, epsa, gamma = TIO.read_ftoddump(_text(self, "file"))
+        except FileNotFoundError:
+            raise SisiException("Failed to open file")
+        except TIO.TensorFormatError as e:
+            raise SisiException(str(e))
+        for key, val in (("HoleEigenEnergies", epsi), ("ParticleEigenEnergies", epsa), ("CoulombVertex", gamma)):
+            if self.isArgumentGiven(key):
+                self.data[_data_name(self, key)] = val
+
+
+@register
 class UegVertexGenerator(Algorithm):
     """Counterpart of reference src/algorithms/UegVertexGenerator.cxx:51-229 (arguments No, Nv, rs;
     outputs CoulombVertex, HoleEigenEnergies, ParticleEigenEnergies).  The vertex is written in real

@@ -106,7 +106,8 @@ class DeviceTensors:
         return t
 
     def upload(self, t: Tensor, data):
-        a = np.asfortranarray(data, dtype=np.float64)
+        a = np.asarray(data, dtype=np.float64)
+        a = np.asfortranarray(a) if a.ndim else np.ascontiguousarray(a).reshape(())   # asfortranarray makes 0-d arrays 1-d
         if tuple(a.shape) != t.shape:
             raise ValueError(f"expected shape {t.shape}, got {a.shape}")
         self._chk(self.lib.tn_upload(self._h, t.id, a.ctypes.data_as(_DP)))

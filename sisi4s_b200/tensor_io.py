@@ -93,8 +93,13 @@ def _default_order(n):
 
 def write_text(path: str, a: np.ndarray, name: str = "Data", row_index_order: str = "",
                column_index_order: str = "", delimiter: str = " ") -> None:
-    """TensorIo::writeText (TensorIo.cxx:157-226)."""
-    a = np.asarray(a, dtype=np.float64)
+    """TensorIo::writeText (TensorIo.cxx:157-226).  Complex tensors are written the way the reference's
+    `file << values[i]` prints a std::complex: "(re,im)"."""
+    a = np.asarray(a)
+    cplx = np.iscomplexobj(a)
+    a = a.astype(np.complex128 if cplx else np.float64)
+    if cplx and "," in delimiter:
+        raise TensorFormatError('complex values are written as "(re,im)": the delimiter must not contain ","')
     if row_index_order == "" and column_index_order == "":
         row_index_order = _default_order(a.ndim)
     if len(row_index_order) + len(column_index_order) != a.ndim:
@@ -103,27 +108,41 @@ def write_text(path: str, a: np.ndarray, name: str = "Data", row_index_order: st
     b = np.transpose(a, [ord(c) - ord("i") for c in stored])       # B[stored] = A[ijk..]
     ncol = int(np.prod([a.shape[ord(c) - ord("i")] for c in column_index_order], dtype=np.int64))
     values = np.asfortranarray(b).reshape(-1, order="F")
+    fmt = (lambda x: f"({x.real:.16g},{x.imag:.16g})") if cplx else (lambda x: f"{x:.16g}")
     with open(path, "w") as f:
         f.write(delimiter.join([name, str(a.ndim)] + [str(n) for n in a.shape]) + "\n")
         f.write(row_index_order + delimiter + column_index_order + "\n")
         for r in range(values.size // max(ncol, 1)):
-            f.write(delimiter.join(f"{x:.16g}" for x in values[r * ncol:(r + 1) * ncol]) + "\n")
+            f.write(delimiter.join(fmt(x) for x in values[r * ncol:(r + 1) * ncol]) + "\n")
 
 
 def read_text(path: str, delimiter: str = " "):
-    """TensorIo::readText (TensorIo.cxx:38-117): returns (name, array in the declared order)."""
+    """TensorIo::readText (TensorIo.cxx:38-117): returns (name, array in the declared order).  The
+    reference splits the two header lines at blanks and scans numbers with strtod (Scanner.hpp:85-112),
+    i.e. it reads blank-delimited files; here any `delimiter` a file was written with is accepted as
+    well, and "(re,im)" values give a complex tensor."""
     if not os.path.exists(path):
         raise FileNotFoundError(f'Failed to open file "{path}"')
+    blank = (lambda t: t.replace(delimiter, " ")) if delimiter.strip() else (lambda t: t)
     with open(path) as f:
-        head = f.readline().split()
+        head = blank(f.readline()).split()
+        if len(head) < 2:
+            raise TensorFormatError("Invalid header line")
         name, order = head[0], int(head[1])
         lens = [int(x) for x in head[2:2 + order]]
-        orders = f.readline().rstrip("\n").split(delimiter) if delimiter != " " else f.readline().split()
+        if len(lens) != order:
+            raise TensorFormatError("Invalid header line")
+        orders = blank(f.readline().rstrip("\n")).split()
         row = orders[0] if orders else ""
         col = orders[1] if len(orders) > 1 else ""
-        if len(row) + len(col) != order:        # "ijk " (empty column order) splits into one token
-            row, col = (orders[0], "") if len(orders[0]) == order else (row, col)
-        values = np.array(f.read().replace(delimiter, " ").split(), dtype=np.float64)
+        if len(row) + len(col) != order:
+            raise TensorFormatError("Number of indices in rowIndexOrder and columnIndexOrder must match tensor order")
+        body = f.read()
+    if "(" in body:           # NumberScanner<Complex> (Scanner.hpp:95-112)
+        flat = np.array(body.replace("(", " ").replace(")", " ").replace(",", " ").split(), dtype=np.float64)
+        values = flat[0::2] + 1j * flat[1::2]
+    else:
+        values = np.array(blank(body).split(), dtype=np.float64)
     stored = col + row
     stored_lens = [lens[ord(c) - ord("i")] for c in stored]
     if values.size != int(np.prod(stored_lens, dtype=np.int64)):
@@ -131,6 +150,71 @@ def read_text(path: str, delimiter: str = " "):
     b = values.reshape(stored_lens, order="F")
     a = np.transpose(b, [stored.index(c) for c in _default_order(order)])   # A[ijk..] = B[stored]
     return name, np.asfortranarray(a)
+
+
+# ---- legacy FTODDUMP: Coulomb vertex + eigenenergies in one chunked binary file
+#      (reference src/algorithms/CoulombVertexReader.hpp:33-51, .cxx:12-15,27-108)
+FTOD_MAGIC = b"sisi4sFT"            # first 8 characters of Header::MAGIC "sisi4sFTOD" (strncmp over 8)
+FTOD_REALS, FTOD_IMAGS, FTOD_EPSILONS = b"FTODreal", b"FTODimag", b"FTODepsi"
+_FTOD_HEADER = struct.Struct("<8s6i")   # magic, No, Nv, NG, NSpins, kPoints, reserved_
+_FTOD_CHUNK = struct.Struct("<8sq")     # magic, size (bytes of the whole chunk, its 16-byte head included)
+
+
+def read_ftoddump(path: str):
+    """CoulombVertexReader::run (:27-108): returns (epsi[No], epsa[Nv], Gamma[NG,Np,Np] complex).  Chunks
+    may come in any order; unknown chunks are skipped, like the reference's loop does."""
+    if not os.path.exists(path):
+        raise FileNotFoundError("Failed to open file")
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        raw = f.read(_FTOD_HEADER.size)
+        if len(raw) < _FTOD_HEADER.size:
+            raise TensorFormatError("Invalid file format")
+        magic, no, nv, ng, _nspins, _kpoints, _ = _FTOD_HEADER.unpack(raw)
+        if magic != FTOD_MAGIC:
+            raise TensorFormatError("Invalid file format")
+        np_ = no + nv
+        n = ng * np_ * np_
+        re = im = eps = None
+        offset = _FTOD_HEADER.size
+        while offset < size:
+            f.seek(offset)
+            head = f.read(_FTOD_CHUNK.size)
+            if len(head) < _FTOD_CHUNK.size:
+                break
+            cmagic, csize = _FTOD_CHUNK.unpack(head)
+            if csize < _FTOD_CHUNK.size:
+                raise TensorFormatError("Invalid chunk size")
+            if cmagic == FTOD_REALS:
+                re = np.fromfile(f, dtype="<f8", count=n)
+            elif cmagic == FTOD_IMAGS:
+                im = np.fromfile(f, dtype="<f8", count=n)
+            elif cmagic == FTOD_EPSILONS:
+                eps = np.fromfile(f, dtype="<f8", count=np_)
+            offset += csize
+    if re is None or re.size != n or eps is None or eps.size != np_:
+        raise TensorFormatError("Invalid file format: vertex or eigenenergy chunk missing")
+    if im is None:
+        im = np.zeros(n)            # the reference leaves a missing chunk's tensor at zero
+    gamma = (re + 1j * im).reshape((ng, np_, np_), order="F")
+    return eps[:no].copy(), eps[no:].copy(), np.asfortranarray(gamma)
+
+
+def write_ftoddump(path: str, epsi, epsa, gamma) -> None:
+    """Writer of the same layout (test infrastructure / data exchange with the reference's reader)."""
+    gamma = np.asarray(gamma)
+    ng, np_, np2 = gamma.shape
+    no, nv = len(epsi), len(epsa)
+    if np_ != np2 or np_ != no + nv:
+        raise ValueError("CoulombVertex must be [NG, No+Nv, No+Nv]")
+    with open(path, "wb") as f:
+        f.write(_FTOD_HEADER.pack(FTOD_MAGIC, no, nv, ng, 1, 1, 0))
+        for magic, data in ((FTOD_REALS, np.asfortranarray(gamma.real).reshape(-1, order="F")),
+                            (FTOD_IMAGS, np.asfortranarray(gamma.imag).reshape(-1, order="F")),
+                            (FTOD_EPSILONS, np.concatenate([np.asarray(epsi, float), np.asarray(epsa, float)]))):
+            data = np.ascontiguousarray(data, dtype="<f8")
+            f.write(_FTOD_CHUNK.pack(magic, _FTOD_CHUNK.size + data.nbytes))
+            f.write(data.tobytes())
 
 
 def read_cc4s(yaml_path: str, mmap: bool = False) -> np.ndarray:

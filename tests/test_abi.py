@@ -29,6 +29,20 @@ def test_header_symbols_all_exported():
         assert hasattr(lib, name), name
 
 
+def test_tensor_engine_header_symbols_all_exported():
+    """include/sisi4s_tn.h (device tensor-contraction engine inside the same shared library)."""
+    _ensure_built()
+    from sisi4s_b200 import tensor_engine as TE
+    with open(os.path.join(ROOT, "include", "sisi4s_tn.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b(tn_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(TE.TN_SYMBOLS), declared ^ set(TE.TN_SYMBOLS)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().pt_estimate_device_bytes(40, 300, 0, 0) > 12e9      # host-only, no GPU needed
+
+
 def test_host_only_entry_points():
     _ensure_built()
     lib = _lib.load()

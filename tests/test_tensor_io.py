@@ -125,3 +125,59 @@ def test_ueg_vertex_generator_step():
         AlgorithmFactory.create("UegVertexGenerator", dict(args, No=5), data).run()
     with pytest.raises(SisiException, match="Invalid rs"):
         AlgorithmFactory.create("UegVertexGenerator", dict(args, rs=0.0), data).run()
+
+
+def test_text_format_complex_and_delimiters(tmp_path):
+    """Advisor r01: complex tensors keep their imaginary part ("(re,im)", the reference's operator<< of
+    std::complex, read back by NumberScanner<Complex>), and a file written with another delimiter
+    reads back."""
+    rng = np.random.default_rng(5)
+    g = np.asfortranarray(rng.standard_normal((3, 4, 2)) + 1j * rng.standard_normal((3, 4, 2)))
+    p = str(tmp_path / "CoulombVertex.dat")
+    TIO.write_text(p, g, "CoulombVertex")
+    name, back = TIO.read_text(p)
+    assert name == "CoulombVertex" and np.iscomplexobj(back) and np.abs(back - g).max() < 1e-15
+    a = np.asfortranarray(rng.standard_normal((4, 5)))
+    TIO.write_text(p, a, "A", row_index_order="i", column_index_order="j", delimiter=",")
+    name, back = TIO.read_text(p, delimiter=",")
+    assert name == "A" and np.abs(back - a).max() < 1e-15
+    with pytest.raises(TIO.TensorFormatError):
+        TIO.write_text(p, g, "G", delimiter=",")
+
+
+def test_ftoddump_reader_follows_the_reference_layout(tmp_path):
+    """Legacy FTODDUMP (CoulombVertexReader.hpp:33-51): 32-byte header `sisi4sFT` + 6 int32, chunks
+    `FTODreal` / `FTODimag` / `FTODepsi` with their total size in bytes, dense column-major doubles."""
+    import struct
+    from sisi4s_b200 import synthetic as S
+    from sisi4s_b200.plan import run_plan_file
+    no, nv, ng = 3, 5, 7
+    gamma = S.make_vertex(no, nv, seed=17, nf=ng)
+    epsi, epsa = S.eigenenergies(no, nv)
+    p = str(tmp_path / "FTODDUMP")
+    TIO.write_ftoddump(p, epsi, epsa, gamma)
+    raw = open(p, "rb").read()
+    assert raw[:8] == b"sisi4sFT" and struct.unpack("<6i", raw[8:32]) == (no, nv, ng, 1, 1, 0)
+    n = ng * (no + nv) ** 2
+    assert raw[32:40] == b"FTODreal" and struct.unpack("<q", raw[40:48])[0] == 16 + 8 * n
+    assert np.frombuffer(raw[48:48 + 8 * n]).tolist() == gamma.real.reshape(-1, order="F").tolist()
+    assert len(raw) == 32 + 2 * (16 + 8 * n) + 16 + 8 * (no + nv)
+    e1, e2, g = TIO.read_ftoddump(p)
+    assert np.array_equal(e1, epsi) and np.array_equal(e2, epsa) and np.array_equal(g, gamma)
+    # chunk order does not matter, unknown chunks are skipped (the reference's while loop, :83-100)
+    chunks = [raw[32:48 + 8 * n], raw[48 + 8 * n:64 + 16 * n], raw[64 + 16 * n:]]
+    odd = b"FTODxxxx" + struct.pack("<q", 16 + 24) + b"\0" * 24
+    open(p, "wb").write(raw[:32] + chunks[2] + odd + chunks[1] + chunks[0])
+    e1, e2, g = TIO.read_ftoddump(p)
+    assert np.array_equal(e1, epsi) and np.array_equal(g, gamma)
+    # as a plan step
+    open(tmp_path / "in.yaml", "w").write(f"""
+- name: CoulombVertexReader
+  in: {{file: "{p}"}}
+  out: {{CoulombVertex: $CoulombVertex, HoleEigenEnergies: $HoleEigenEnergies, ParticleEigenEnergies: $ParticleEigenEnergies}}
+""")
+    data = run_plan_file(str(tmp_path / "in.yaml"), log=lambda *_: None)
+    assert np.array_equal(data["CoulombVertex"], gamma) and np.array_equal(data["ParticleEigenEnergies"], epsa)
+    open(p, "wb").write(b"notafile" + raw[8:])
+    with pytest.raises(TIO.TensorFormatError, match="Invalid file format"):
+        TIO.read_ftoddump(p)
