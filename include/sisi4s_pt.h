@@ -149,7 +149,12 @@ int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double *slab);
 /* The whole PPPHCoulombIntegrals[v,v,v,o] tensor in caller-owned HOST memory.
  * Without slab_slots it is uploaded at once (= pt_set_ppph_slabs(h,0,o,..)).
  * With slab_slots < o only the pointer is recorded: it must stay valid until
- * pt_destroy, and pt_run uploads the slabs its current hole blocks need.       */
+ * pt_destroy, and pt_run uploads the slabs its current hole blocks need.
+ * With "async_upload" = 1 (and everything resident) the upload is deferred to
+ * pt_run as well: only the slabs of the holes its triples touch are copied
+ * (a rank of a multi-GPU run needs the slabs k >= its smallest hole only), on
+ * a second stream, and the triples run in waves ordered by their largest hole
+ * so that all but the first small wave's copies hide behind the kernel.       */
 int pt_set_ppph_host(pt_handle_t h, const double *vabci);
 /* Alternative to pt_set_ppph_slabs: CoulombVertex Gamma[NF,Np,Np] complex,
  * given as separate real and imaginary parts (fromComplexTensor,

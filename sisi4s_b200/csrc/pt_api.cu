@@ -96,6 +96,12 @@ struct PtHandle_ {
   double* gp = nullptr;
   int g_nf = 0, g_np = 0;
   const double* host_ppph = nullptr;        // caller-owned PPPHCoulombIntegrals[v,v,v,o]
+  // all-resident engines with asynchronous setters: the slabs of a host PPPH tensor are uploaded by pt_run,
+  // only those its triples touch, on a second stream while earlier waves of triples already compute
+  bool lazy_ppph = false;
+  cudaStream_t copy_stream = nullptr;
+  double* wave_stage = nullptr;  // raw slabs in flight
+  size_t cap_wave = 0;
   // hole-block mode (option hole_block = b: BASELINE configs[4]): T2 / PPHH stay in caller-owned host
   // memory, the sorted triples are walked by hole-block triples (I<=J<=K), each group's <= 3b active
   // holes are staged into the buffers above (sized for 3b holes once) before its launch
@@ -409,6 +415,8 @@ int pt_destroy(pt_handle_t h) {
   if (h->d_hmap) cudaFree(h->d_hmap);
   if (h->d_sync) cudaFree(h->d_sync);
   if (h->d_list) cudaFree(h->d_list);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->wave_stage) cudaFree(h->wave_stage);
   for (void* p : h->registered) cudaHostUnregister(p);
   for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev_up0, h->ev_up1})
     if (ev) cudaEventDestroy(ev);
@@ -656,9 +664,10 @@ int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
 
 int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
   if (!h || !vabci) return fail(PT_ERR_INVALID, "pt_set_ppph_host: null");
-  if (!h->blocked()) return pt_set_ppph_slabs(h, 0, h->oh(), vabci);
+  if (!h->blocked() && !(h->async_upload && !h->keep_raw && !h->hole_block)) return pt_set_ppph_slabs(h, 0, h->oh(), vabci);
   CU(cudaSetDevice(h->device));
-  RC(ensure_ppph_buffers(h, true));
+  RC(ensure_ppph_buffers(h, h->blocked()));
+  h->lazy_ppph = !h->blocked();   // everything fits: pt_run uploads the slabs its triples touch, in waves
   h->host_ppph = vabci;
   pin(h, vabci, (size_t)h->d.v * h->d.v * h->d.v * h->oh());
   std::fill(h->slab_set.begin(), h->slab_set.end(), 1);
@@ -998,16 +1007,39 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
     const bool grouped = h->blocked() || h->hole_block;
     const int bw = h->hole_block ? h->hole_block : (h->blocked() ? h->nslots() / 3 : o);
     const long long nb = (o + bw - 1) / bw;
+    // Lazy upload of a host PPPH tensor (all-resident engine, asynchronous setters): only the slabs of the
+    // holes these triples touch are uploaded, in ascending hole order on the copy stream, and the triples
+    // run in WAVES -- wave w = the triples whose largest hole k lies among the first c_w missing slabs
+    // (i <= j <= k, so their other slabs came earlier) -- so that all but the first small wave's upload
+    // hides behind the kernel.  wave_of[z] = wave that makes slab z resident (-1: already there).
+    std::vector<int> wave_of, wave_end;   // wave_end[w] = number of missing slabs loaded up to wave w
+    std::vector<int> missing;
+    if (!grouped && h->lazy_ppph) {
+      std::vector<char> touched(o, 0);
+      for (auto& t : tr)
+        if (triple_class(t) != 3) touched[t.i] = touched[t.j] = touched[t.k] = 1;
+      for (int z = 0; z < o; ++z)
+        if (touched[z] && h->slot_of[z] < 0) missing.push_back(z);
+      wave_of.assign(o, -1);
+      const int m = (int)missing.size();
+      for (int c : {(m + 7) / 8, (m + 3) / 4, (m + 1) / 2, m})
+        if (c > 0 && (wave_end.empty() || c > wave_end.back())) wave_end.push_back(c);
+      for (int q = 0, w = 0; q < m; ++q) {
+        while (q >= wave_end[w]) ++w;
+        wave_of[missing[q]] = w;
+      }
+    }
     for (size_t n = 0; n < tr.size(); ++n) {
       const int c = triple_class(tr[n]);
       if (c == 3) continue;
-      const long long key = grouped ? ((long long)(tr[n].i / bw) * nb + tr[n].j / bw) * nb + tr[n].k / bw : 0;
+      long long key = grouped ? ((long long)(tr[n].i / bw) * nb + tr[n].j / bw) * nb + tr[n].k / bw : 0;
+      if (!missing.empty()) key = std::max(0, std::max(wave_of[tr[n].i], std::max(wave_of[tr[n].j], wave_of[tr[n].k])));
       ent.push_back({make_int4(tr[n].i, tr[n].j, tr[n].k, c), (int)n, key});
     }
     // equal-cost items: within a group generic triples (i<j<k) first, then i=j, then j=k (stable:
     // consecutive entries keep sharing their leading holes).  CTAs that all run equal-cost items stay
     // in step, so the PPPH tiles they share are read within the L2's residency window.
-    if (grouped || h->class_sort)
+    if (grouped || !missing.empty() || h->class_sort)
       std::stable_sort(ent.begin(), ent.end(), [&](const Entry& a, const Entry& b) {
         if (a.key != b.key) return a.key < b.key;
         return h->class_sort ? a.t.w < b.t.w : false;
@@ -1063,6 +1095,31 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
       PT_TRACE("scratch ready");
       CU(cudaMemcpyAsync(h->d_list, list.data(), list.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
       PT_TRACE("lists ready");
+      // waves: slab copies go to the copy stream, into the raw staging area, one event per wave.  Wave 0 is
+      // issued now, wave w + 1 right after the kernel of wave w has been launched (with pageable host
+      // memory a copy blocks the calling thread, so it must not be issued ahead of that launch).
+      std::vector<cudaEvent_t> wev(wave_end.size(), nullptr);
+      struct WevGuard { std::vector<cudaEvent_t>& v; ~WevGuard() { for (auto e : v) if (e) cudaEventDestroy(e); } } wevguard{wev};
+      size_t waves_issued = 0;
+      const size_t slab3 = (size_t)h->d.v * h->d.v * h->d.v;
+      auto issue_waves = [&](size_t upto) -> int {   // enqueue the copies of all waves < upto
+        for (; waves_issued < std::min(upto, wave_end.size()); ++waves_issued) {
+          const size_t w = waves_issued;
+          for (size_t q = w ? wave_end[w - 1] : 0; q < (size_t)wave_end[w]; ++q) {
+            CU(cudaMemcpyAsync(h->wave_stage + slab3 * q, h->host_ppph + slab3 * (size_t)missing[q], slab3 * sizeof(double),
+                               cudaMemcpyHostToDevice, h->copy_stream));
+            h->stats.bytes_h2d += (double)(slab3 * sizeof(double));
+          }
+          CU(cudaEventCreateWithFlags(&wev[w], cudaEventDisableTiming));
+          CU(cudaEventRecord(wev[w], h->copy_stream));
+        }
+        return PT_OK;
+      };
+      if (!missing.empty()) {
+        if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(h->grow(&h->wave_stage, &h->cap_wave, slab3 * missing.size()));
+        RC(issue_waves(1));
+      }
       std::vector<cudaEvent_t> kev(2 * groups.size(), nullptr);
       struct EvGuard { std::vector<cudaEvent_t>& v; ~EvGuard() { for (auto e : v) if (e) cudaEventDestroy(e); } } evguard{kev};
       for (auto& ev : kev) CU(cudaEventCreate(&ev));
@@ -1072,6 +1129,20 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
         if (h->hole_block) {
           RC(stage_group(h, g.holes));
           p.d = make_dims((int)g.holes.size(), h->d.v, h->o_full);
+        }
+        const int wave = missing.empty() ? -1 : (int)ent[g.g0].key;
+        if (wave >= 0) {
+          // the slabs up to this wave have arrived (or the stream waits for them): pack them into their slots
+          RC(issue_waves((size_t)wave + 1));
+          for (int ww = 0; ww <= wave; ++ww) {     // waves without triples of their own still have to be packed
+            if (!wev[ww]) continue;
+            CU(cudaStreamWaitEvent(h->stream, wev[ww], 0));
+            for (int q = ww ? wave_end[ww - 1] : 0; q < wave_end[ww]; ++q)
+              RC(pack_into_slot(h, h->wave_stage + slab3 * (size_t)q, missing[q], missing[q]));
+            h->stats.slab_loads += wave_end[ww] - (ww ? wave_end[ww - 1] : 0);
+            CU(cudaEventDestroy(wev[ww]));
+            wev[ww] = nullptr;
+          }
         }
         if (grouped) {
           if (h->blocked()) RC(ensure_slabs(h, g.holes));
@@ -1102,6 +1173,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
         CU(launch_fused(p, grid, h->stream));
         PT_TRACE("launched");
         CU(cudaEventRecord(kev[2 * gi + 1], h->stream));
+        if (wave >= 0) RC(issue_waves((size_t)wave + 2));   // the next wave's copies run behind this kernel
         PT_TRACE("fused kernel done");
         CU(launch_reduce_items(h->d_item, p.ntriples, h->norbits, p.order, h->d_e + g.g0, h->stream));
         h->stats.kernel_launches += 2;

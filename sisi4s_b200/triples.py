@@ -77,6 +77,7 @@ class TriplesEngine:
         if pin_host:
             self.set_option("pin_host", 1)
         self.async_upload = bool(async_upload)
+        self.keep_raw = bool(keep_raw)
         self.set_option("keep_raw", int(keep_raw))
         self.set_option("engine", int(engine))
         if grid:
@@ -395,7 +396,9 @@ class CcsdPerturbativeTriples(Algorithm):
             eng.set_hhhp(self.getTensorArgument("HHHPCoulombIntegrals"))
         if self.isArgumentGiven("PPPHCoulombIntegrals"):
             ppph = self.getTensorArgument("PPPHCoulombIntegrals")
-            if eng.hole_block or self.getIntegerArgument("slabSlots", 0):
+            if eng.hole_block or self.getIntegerArgument("slabSlots", 0) or (eng.async_upload and not eng.keep_raw):
+                # the tensor stays with the caller: blocked modes fetch slabs on demand; an all-resident engine
+                # with asynchronous setters uploads only the slabs its triples touch, behind the first kernels
                 eng.set_ppph_host(ppph)
             else:
                 eng.set_ppph(ppph)

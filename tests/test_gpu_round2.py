@@ -199,3 +199,28 @@ def test_async_setters_give_the_same_energy():
         res = eng.run()          # pt_run waits for the enqueued uploads itself
         assert eng.stats().seconds_upload > 0
     assert np.array_equal(res.per_triple, base.per_triple)
+
+
+def test_lazy_ppph_upload_in_waves_is_bitwise_the_eager_run():
+    """Asynchronous setters + pt_set_ppph_host on an all-resident engine: pt_run uploads only the slabs its
+    triples touch, on the copy stream, and runs the triples in waves ordered by their largest hole."""
+    o, v = 9, 37
+    inp = S.make_inputs(o, v, seed=2026, kind="random")
+    with TriplesEngine(o, v) as eng:
+        eng.set_inputs(*inp.args())
+        base = eng.run().per_triple
+    with TriplesEngine(o, v, async_upload=True) as eng:
+        eng.set_eigenenergies(inp.epsi, inp.epsa); eng.set_singles(inp.T1); eng.set_doubles(inp.T2)
+        eng.set_pphh(inp.Vpphh); eng.set_hhhp(inp.Vhhhp)
+        eng.set_ppph_host(inp.Vppph)
+        b, e = eng.partition(3, 2)                      # the last third: small holes are never touched
+        tr = _triples(o)
+        part = eng.run(b, e)
+        assert np.array_equal(part.per_triple, base[b:e])
+        touched = {h for t in tr[b:e] for h in t if len(set(t)) > 1}
+        assert eng.stats().slab_loads == len(touched) < o
+        full = eng.run()                                # the remaining slabs arrive now
+        assert np.array_equal(full.per_triple, base)
+        assert eng.stats().slab_loads == o
+        assert np.array_equal(eng.run_list([5, 100, 17]).per_triple, base[[5, 100, 17]])
+        assert eng.stats().slab_loads == o              # nothing left to load
