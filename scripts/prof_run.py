@@ -2,7 +2,8 @@
 range of sorted triples (cold start, inputs resident)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from sisi4s_b200 import synthetic as S
+import torch
+import bench
 from sisi4s_b200.triples import TriplesEngine
 
 # "step P" = the bench's step P (partition P of 8); otherwise <first triple> <count>
@@ -11,7 +12,8 @@ b = 5000 if step or len(sys.argv) <= 1 else int(sys.argv[1])
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 order = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 tile_holes = int(sys.argv[4]) if len(sys.argv) > 4 else None
-inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
+host = bench.HostBuffers(False, 0, lambda: None, "prof")
+inp = bench.generate_inputs(bench.WORKLOADS["o40v300"], torch.device("cuda", 0), host, 0, 1)   # the bench's inputs
 with TriplesEngine(40, 300) as eng:
     eng.set_inputs(*inp.args())
     eng.set_option("order", order)
