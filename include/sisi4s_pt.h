@@ -115,7 +115,10 @@ const char *pt_version(void);
  * valid and unmodified until pt_sync or pt_run returns.  0 (default): every
  * setter returns after its copy has completed);
  * "pin_host" (1: page-lock the caller's large tensors in hole_block mode so
- * the per-group block copies run at full DMA speed).                          */
+ * the per-group block copies run at full DMA speed);
+ * "particle_contraction" (vd: length of the particle contraction sum_d when it differs from v --
+ * the doubles then have shape [v,vd,o,o] and the PPPH slabs [v,v,vd]; used by the complex triples
+ * driver, which stacks real and imaginary parts along d; set before any input).              */
 int pt_set_option(pt_handle_t h, const char *key, int64_t value);
 /* waits for everything the setters enqueued (async_upload) and reports their errors */
 int pt_sync(pt_handle_t h);
@@ -131,6 +134,11 @@ int64_t pt_estimate_device_bytes(int o, int v, int slab_slots, int hole_block);
 int pt_set_eigenenergies(pt_handle_t h, const double *epsi, const double *epsa);
 /* CcsdSinglesAmplitudes[v,o]  ("ai", ClusterSinglesDoublesAlgorithm.cxx:42-45) */
 int pt_set_singles(pt_handle_t h, const double *t1);
+/* Optional SECOND singles term: the step then uses S = 1/2 (T1 (x) PPHH + t1b (x) vabij_b) in
+ * getSinglesContribution (same shapes as pt_set_singles / pt_set_pphh).  The complex closed-shell
+ * step (reference CcsdPerturbativeTriplesComplex.cxx:142-148) needs it: the real part of
+ * 1/2 Tai Vabij is 1/2 (Re T Re V - Im T Im V).                                   */
+int pt_set_singles_pair(pt_handle_t h, const double *t1b, const double *vabij_b);
 /* CcsdDoublesAmplitudes[v,v,o,o] ("abij")                                     */
 int pt_set_doubles(pt_handle_t h, const double *t2);
 /* pt_create_ex engines only: the doubles amplitudes of the HOLE term, T2[a,b,x,l] with x over

@@ -51,6 +51,7 @@ SYMBOLS = {
     "pt_vertex_integrals": (C.c_int, [_H, C.c_char_p, _DP]),
     "pt_set_eigenenergies": (C.c_int, [_H, _DP, _DP]),
     "pt_set_singles": (C.c_int, [_H, _DP]),
+    "pt_set_singles_pair": (C.c_int, [_H, _DP, _DP]),
     "pt_set_doubles": (C.c_int, [_H, _DP]),
     "pt_set_doubles_hole": (C.c_int, [_H, _DP]),
     "pt_set_pphh": (C.c_int, [_H, _DP]),

@@ -79,6 +79,7 @@ struct PtHandle_ {
   bool up_pending = false, up_started = false;
   // raw device tensors
   double *epsi = nullptr, *epsa = nullptr, *t1 = nullptr, *pphh = nullptr, *qsum = nullptr;
+  double *t1b = nullptr, *pphhb = nullptr, *qsumb = nullptr;   // optional second singles term (pt_set_singles_pair)
   double *t2_raw = nullptr, *hhhp_raw = nullptr, *ppph_raw = nullptr;  // keep_raw only (hhhp_raw also: hole-block mode)
   // packed
   double *Tt = nullptr, *T2h = nullptr, *Vt = nullptr, *Ut = nullptr;
@@ -406,7 +407,7 @@ int pt_destroy(pt_handle_t h) {
   if (!h) return PT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  double* ptrs[] = {h->epsi, h->epsa, h->t1, h->pphh, h->qsum, h->t2_raw, h->hhhp_raw, h->ppph_raw,
+  double* ptrs[] = {h->t1b, h->pphhb, h->qsumb, h->epsi, h->epsa, h->t1, h->pphh, h->qsum, h->t2_raw, h->hhhp_raw, h->ppph_raw,
                     h->Tt, h->T2h, h->Vt, h->Ut, h->slab_stage, h->gp, h->stage_raw, h->d_e, h->d_item};
   for (double* p : ptrs)
     if (p) cudaFree(p);
@@ -452,6 +453,11 @@ int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
     if (h->hole_block > 0 && (h->slab_slots == 0 || h->slab_slots < oa)) h->slab_slots = oa;
     h->slab_set.assign(h->oh(), 0);
     h->slot_of.assign(h->oh(), -1);
+  } else if (!strcmp(key, "particle_contraction")) {
+    if (value < 1) return fail(PT_ERR_INVALID, "particle_contraction %lld", (long long)value);
+    if (any_input) return fail(PT_ERR_INVALID, "particle_contraction must be set before any input tensor");
+    if (h->hole_block) return fail(PT_ERR_UNSUPPORTED, "particle_contraction and hole_block are mutually exclusive");
+    h->d = make_dims(h->d.o, h->d.v, h->d.ol, (int)value);
   } else if (!strcmp(key, "async_upload")) {
     h->async_upload = value != 0;
   } else if (!strcmp(key, "pin_host")) {
@@ -532,11 +538,28 @@ int pt_set_pphh(pt_handle_t h, const double* vabij) {
   return PT_OK;
 }
 
+int pt_set_singles_pair(pt_handle_t h, const double* t1b, const double* vabij_b) {
+  if (!h || !t1b || !vabij_b) return fail(PT_ERR_INVALID, "pt_set_singles_pair: null");
+  if (h->hole_block) return fail(PT_ERR_UNSUPPORTED, "pt_set_singles_pair: not in hole_block mode");
+  CU(cudaSetDevice(h->device));
+  UploadScope up(h);
+  const size_t n1 = (size_t)h->d.v * h->d.o, n = (size_t)h->d.v * h->d.v * h->d.o * h->d.o;
+  if (!h->t1b) CU(h->alloc(&h->t1b, n1));
+  if (!h->pphhb) CU(h->alloc(&h->pphhb, n));
+  if (!h->qsumb) CU(h->alloc(&h->qsumb, n));
+  RC(upload(h, h->t1b, t1b, n1));
+  RC(upload(h, h->pphhb, vabij_b, n));
+  CU(launch_pphh_symsum(h->pphhb, h->qsumb, h->d, h->stream));
+  h->stats.kernel_launches += 1;
+  RC(up.done());
+  return PT_OK;
+}
+
 int pt_set_doubles(pt_handle_t h, const double* t2) {
   if (!h || !t2) return fail(PT_ERR_INVALID, "pt_set_doubles: null");
   CU(cudaSetDevice(h->device));
   UploadScope up(h);
-  const size_t n = (size_t)h->d.v * h->d.v * h->d.o * h->d.o;
+  const size_t n = (size_t)h->d.v * h->d.vd * h->d.o * h->d.o;
   if (!h->Tt) CU(h->alloc(&h->Tt, tt_elems(h->d)));
   if (h->hole_block) {
     if (!h->T2h) CU(h->alloc(&h->T2h, t2h_elems(h->d)));
@@ -614,7 +637,7 @@ int pt_set_hhhp(pt_handle_t h, const double* vijka) {
 }
 
 static int ensure_ppph_buffers(pt_handle_t h, bool need_stage) {
-  const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+  const size_t slab = (size_t)h->d.v * h->d.v * h->d.vd;
   if (h->blocked() && h->keep_raw) return fail(PT_ERR_INVALID, "slab_slots / hole_block and keep_raw are mutually exclusive");
   if (!h->Vt) {
     CU(h->alloc(&h->Vt, vt_slab_elems(h->d) * (size_t)h->nslots()));
@@ -651,7 +674,7 @@ int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
   CU(cudaSetDevice(h->device));
   RC(ensure_ppph_buffers(h, true));
   UploadScope up(h);
-  const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+  const size_t slab = (size_t)h->d.v * h->d.v * h->d.vd;
   for (int k = k0; k < k1; ++k) {
     double* dst = h->keep_raw ? h->ppph_raw + slab * k : h->slab_stage;
     RC(upload(h, dst, slabs + slab * (size_t)(k - k0), slab));
@@ -669,7 +692,7 @@ int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
   RC(ensure_ppph_buffers(h, h->blocked()));
   h->lazy_ppph = !h->blocked();   // everything fits: pt_run uploads the slabs its triples touch, in waves
   h->host_ppph = vabci;
-  pin(h, vabci, (size_t)h->d.v * h->d.v * h->d.v * h->oh());
+  pin(h, vabci, (size_t)h->d.v * h->d.v * h->d.vd * h->oh());
   std::fill(h->slab_set.begin(), h->slab_set.end(), 1);
   std::fill(h->slot_of.begin(), h->slot_of.end(), -1);
   std::fill(h->hole_in.begin(), h->hole_in.end(), -1);
@@ -679,6 +702,7 @@ int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
 int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double* gim) {
   if (!h || !gre || !gim) return fail(PT_ERR_INVALID, "pt_set_vertex: null");
   if (nf < 1 || np < h->oh() + h->d.v) return fail(PT_ERR_INVALID, "pt_set_vertex: nf=%d np=%d (o+v=%d)", nf, np, h->oh() + h->d.v);
+  if (h->d.vd != h->d.v) return fail(PT_ERR_UNSUPPORTED, "pt_set_vertex: not with a stacked particle contraction");
   CU(cudaSetDevice(h->device));
   RC(ensure_ppph_buffers(h, false));
   UploadScope up(h);
@@ -708,7 +732,7 @@ int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double
   std::fill(h->hole_in.begin(), h->hole_in.end(), -1);
   if (!h->blocked()) {
     // all slabs resident: build them now, straight into the packed layout
-    const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+    const size_t slab = (size_t)h->d.v * h->d.v * h->d.vd;
     for (int k = 0; k < h->oh(); ++k) {
       RC(build_slab_packed(h, k, h->Vt + vt_slab_elems(h->d) * (size_t)k));
       note_slot(h, k, k);
@@ -796,7 +820,7 @@ int pt_vertex_integrals(pt_handle_t h, const char* block, double* out) {
 // blocked mode: make the slabs of all holes in `need` resident (LRU replacement among the slots
 // that hold none of them), then publish the active hole -> slot table to the device
 static int ensure_slabs(pt_handle_t h, const std::vector<int>& need) {
-  const size_t slab = (size_t)h->d.v * h->d.v * h->d.v;
+  const size_t slab = (size_t)h->d.v * h->d.v * h->d.vd;
   std::vector<char> pinned(h->nslots(), 0);
   for (int z : need)
     if (h->slot_of[z] >= 0) { pinned[h->slot_of[z]] = 1; h->slot_tick[h->slot_of[z]] = ++h->tick; }
@@ -901,6 +925,7 @@ static FusedParams make_params(pt_handle_t h) {
   p.d = h->d;
   p.Tt = h->Tt; p.T2h = h->T2h; p.Vt = h->Vt; p.Ut = h->Ut;
   p.t1 = h->t1; p.pphh = h->pphh; p.qsum = h->qsum; p.epsi = h->epsi; p.epsa = h->epsa;
+  p.t1b = h->t1b; p.pphhb = h->pphhb; p.qsumb = h->qsumb;
   p.orbits = h->d_orbits;
   p.norbits = h->norbits;
   return p;
@@ -909,7 +934,7 @@ static FusedParams make_params(pt_handle_t h) {
 static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<double>& e_out) {
   if (!h->t2_raw || !h->ppph_raw || !h->hhhp_raw)
     return fail(PT_ERR_INVALID, "PT_ENGINE_NAIVE needs option keep_raw=1 set before the tensors");
-  if (h->d.ol != h->d.o) return fail(PT_ERR_UNSUPPORTED, "PT_ENGINE_NAIVE needs o_act == o_all");
+  if (h->d.ol != h->d.o || h->d.vd != h->d.v) return fail(PT_ERR_UNSUPPORTED, "PT_ENGINE_NAIVE needs o_act == o_all and no stacked contraction");
   const size_t n3 = (size_t)h->d.v * h->d.v * h->d.v;
   StreamScratch<double> w, d_e;
   CU(w.alloc(6 * n3, h->stream));
@@ -1101,7 +1126,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
       std::vector<cudaEvent_t> wev(wave_end.size(), nullptr);
       struct WevGuard { std::vector<cudaEvent_t>& v; ~WevGuard() { for (auto e : v) if (e) cudaEventDestroy(e); } } wevguard{wev};
       size_t waves_issued = 0;
-      const size_t slab3 = (size_t)h->d.v * h->d.v * h->d.v;
+      const size_t slab3 = (size_t)h->d.v * h->d.v * h->d.vd;
       auto issue_waves = [&](size_t upto) -> int {   // enqueue the copies of all waves < upto
         for (; waves_issued < std::min(upto, wave_end.size()); ++waves_issued) {
           const size_t w = waves_issued;
@@ -1204,8 +1229,8 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
   for (double x : e) sum += (long double)x;
   *e_triples = (double)sum;
   if (e_per_triple) std::copy(e.begin(), e.end(), e_per_triple);
-  const double of = h->d.ol, v = h->d.v;
-  h->stats.flops_algorithmic = 2.0 * v * v * v * (v + of) * (double)weight;
+  const double of = h->d.ol, v = h->d.v, vd = h->d.vd;
+  h->stats.flops_algorithmic = 2.0 * v * v * v * (vd + of) * (double)weight;
   h->stats.triples_run = (int64_t)tr.size();
   return PT_OK;
 }

@@ -7,7 +7,7 @@
 // copies and every DMMA fragment load is a conflict-free 256-byte warp read.
 //
 //   TILE = 16 particle indices per range, nr = ceil(v/16) ranges, vp = 16 nr
-//   nk4 = ceil(v/4) chunks of the particle contraction index d
+//   nk4 = ceil(vd/4) chunks of the particle contraction index d (vd = v unless Re/Im parts are stacked)
 //   nl4 = ceil(ol/4) chunks of the hole contraction index l (ol = o unless pt_create_ex)
 //
 //   Vt [z][Q][R][dc][n=256][kk=4]      = Vppph[b=16Q+n/16, c=16R+n%16, d=4dc+kk, z]
@@ -39,20 +39,23 @@ constexpr int FUSED_THREADS = (NCONSUMER_WARPS + NPRODUCER_WARPS) * 32;
 struct Dims {
   int o, v;  // ACTIVE holes (the hole indices of the triples that are run), particles
   int ol;    // holes of the contraction sum_l of getDoublesContribution; = o unless the engine holds a
-             // hole SUBSET of a larger problem (pt_create_ex)
+             // hole SUBSET of a larger problem (pt_create_ex) or a stacked complex problem
+  int vd;    // length of the particle contraction sum_d; = v unless real and imaginary parts are
+             // stacked along d (complex triples: W_re = [T_re | -T_im] . [V_re ; V_im])
   int nr;    // particle ranges
   int vp;    // 16*nr
   int nk4;   // ceil(v/4)
   int nl4;   // ceil(o/4)
 };
 
-__host__ __device__ inline Dims make_dims(int o, int v, int ol = 0) {
+__host__ __device__ inline Dims make_dims(int o, int v, int ol = 0, int vd = 0) {
   Dims d;
   d.o = o; d.v = v;
   d.ol = ol > 0 ? ol : o;
+  d.vd = vd > 0 ? vd : v;
   d.nr = (v + TILE - 1) / TILE;
   d.vp = d.nr * TILE;
-  d.nk4 = (v + 3) / 4;
+  d.nk4 = (d.vd + 3) / 4;
   d.nl4 = (d.ol + 3) / 4;
   return d;
 }
@@ -87,6 +90,11 @@ struct FusedParams {
   const double* t1;    // raw [v,o]
   const double* pphh;  // raw [v,v,o,o]
   const double* qsum;  // pphh[b,c,j,k] + pphh[c,b,k,j], same layout
+  // optional SECOND singles term (complex triples: S_re = 1/2 (t_re P_re - t_im P_im) is a sum of two
+  // outer products): Sd += 1/2 t1b (x) pphhb, same layouts; nullptr = one term
+  const double* t1b;
+  const double* pphhb;
+  const double* qsumb;
   const double* epsi;
   const double* epsa;
   const int4* triples;    // (i,j,k,class) of the sorted triples of this run

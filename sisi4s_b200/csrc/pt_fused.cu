@@ -598,6 +598,7 @@ __device__ __forceinline__ void scatter_add(double* stg, uint32_t tmem_lane_base
 //   Sd = 1/2 (t_i[a] Qa[b,c] + t_j[b] Qb[a,c] + t_k[c] Qc[a,b])
 // (getSinglesContribution, CcsdPerturbativeTriples.cxx:81-85, summed over the distinct hole
 // permutations; pm = mask of those)
+template <int SET = 0>
 __device__ __forceinline__ void epi_stage_load(const FusedParams& p, const PtClassTable& tab, uchar4 ob, int tl,
                                                int hi, int hj, int hk, int pm, int tid, double& sq0,
                                                double& sq1, double& sq2, double& stv0, double& stv1) {
@@ -606,8 +607,9 @@ __device__ __forceinline__ void epi_stage_load(const FusedParams& p, const PtCla
   const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
   const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
   const int u = tid & 15, w_ = tid >> 4;
-  const double* P = p.pphh;
-  const double* S = p.qsum;  // P[b,c,j,k] + P[c,b,k,j]
+  const double* P = SET == 0 ? p.pphh : p.pphhb;
+  const double* S = SET == 0 ? p.qsum : p.qsumb;  // P[b,c,j,k] + P[c,b,k,j]
+  const double* T1 = SET == 0 ? p.t1 : p.t1b;
   const size_t vv = (size_t)v;
   sq0 = sq1 = sq2 = 0.0;
   if (p.debug & 32) return;  // measurement switch: no global loads in the epilogue (wrong results)
@@ -639,7 +641,7 @@ __device__ __forceinline__ void epi_stage_load(const FusedParams& p, const PtCla
     const int which = tid >> 4, uu = tid & 15;
     const int g = (which == 0 ? ga0 : (which == 1 ? gb0 : gc0)) + uu;
     const int hh = which == 0 ? hi : (which == 1 ? hj : hk);
-    stv0 = g < v ? __ldg(p.t1 + g + (size_t)v * hh) : 0.0;
+    stv0 = g < v ? __ldg(T1 + g + (size_t)v * hh) : 0.0;
     stv1 = g < v ? __ldg(p.epsa + g) : 0.0;
   }
 }
@@ -667,7 +669,11 @@ constexpr int FUSED_SMEM_BYTES = (RING_DBL + STG_DBL + 3 * 256 + 96 + 8) * 8 + (
 static_assert(FUSED_SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
 
 // ------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedParams p) {
+// NS = number of singles terms: 1 for the real closed-shell step; 2 adds a second pass of the singles
+// part with (t1b, pphhb) for the stacked complex problem (pt_fused_kernel2; the real kernel's code is
+// not touched by it).
+template <int NS>
+__device__ __forceinline__ void fused_body(const FusedParams& p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Xs, *ring, *stg, *Qs, *tv, *red;
   uint64_t* bars;
@@ -894,6 +900,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
           if (valid01 && x2 < nv2) e_acc += sd * P0[a01 + 256 * x2];
         }
       }
+      if (NS == 2) {
+        // second singles term: sum_x Sd2[x] Y[x] with the operands of set 2, tile by tile
+        for (int tl = 0; tl < 6; ++tl) {
+          double q2[3], t2[2] = {0.0, 0.0};
+          epi_stage_load<1>(p, tab, ob, tl, hi, hj, hk, pm, tid, q2[0], q2[1], q2[2], t2[0], t2[1]);
+          consumer_barrier();                 // the previous readers of the staging buffer are done
+          put_stage(Qb[0], tb[0], q2, t2);
+          consumer_barrier();
+          const double* Qc = Qb[0];
+          const double* tc = tb[0];
+          const int ga0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][0]);
+          const int gb0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][1]);
+          const int gc0 = TILE * sel3(ob.x, ob.y, ob.z, tab.tile_slots[tl][2]);
+          const bool valid01 = (ga0 + x0 < v) && (gb0 + x1 < v);
+          const int nv2 = min(16, v - gc0);
+          const double t0 = 0.5 * tc[x0], t1v = 0.5 * tc[16 + x1];
+          const double q2c = 0.5 * Qc[512 + x0 + 16 * x1];
+          const double* Q0 = Qc + x1;
+          const double* Q1 = Qc + 256 + x0;
+          const double* P0 = Xs + tl * XT_DBL + 16 * x1;
+#pragma unroll
+          for (int x2 = 0; x2 < 16; ++x2) {
+            const int a01 = l01 ^ bitswap13(x2);
+            const double sd = t0 * Q0[16 * x2] + t1v * Q1[16 * x2] + tc[32 + x2] * q2c;
+            if (valid01 && x2 < nv2) e_acc += sd * P0[a01 + 256 * x2];
+          }
+        }
+      }
     } else {
       // ================= degenerate orbits (<= 3 tiles): per tile, six permuted reads per point =================
       double q[3] = {sq[0][0], sq[0][1], sq[0][2]}, t[2] = {stv[0][0], stv[0][1]};
@@ -934,6 +968,29 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
           if (valid01 && x2 < nv2) e_acc += (xd + sd) * zn / dd;
         }
         consumer_barrier();
+        if (NS == 2) {
+          // second singles term of this tile: sum_x Sd2[x] Z[x] / D[x] with the operands of set 2
+          double q2[3], t2[2] = {0.0, 0.0};
+          epi_stage_load<1>(p, tab, ob, tl, hi, hj, hk, pm, tid, q2[0], q2[1], q2[2], t2[0], t2[1]);
+          put_stage(Qs, tv, q2, t2);
+          consumer_barrier();
+          const double t0b = 0.5 * tv[x0], t1b = 0.5 * tv[16 + x1];
+          const double q2b = 0.5 * Qs[512 + x0 + 16 * x1];
+#pragma unroll
+          for (int x2 = 0; x2 < 16; ++x2) {
+            const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
+            double zn = c0 * P0[a01 + 256 * x2];
+            zn += c1 * P1[a01 + 256 * x2];
+            zn += c2 * P2[a25 + 16 * x2];
+            zn += c3 * P3[a34 + 16 * x2];
+            zn += c4 * P4[a34];
+            zn += c5 * P5[a25];
+            const double sd = t0b * Q0[16 * x2] + t1b * Q1[16 * x2] + tv[32 + x2] * q2b;
+            const double dd = d01 - tv[80 + x2];
+            if (valid01 && x2 < nv2) e_acc += sd * zn / dd;
+          }
+          consumer_barrier();
+        }
       }
     }
     // warp-shuffle reduction, then one atomic per item
@@ -959,6 +1016,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedP
   if (warp == 0)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
 }
+
+__global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel(const FusedParams p) { fused_body<1>(p); }
+__global__ void __launch_bounds__(FUSED_THREADS, 1) pt_fused_kernel2(const FusedParams p) { fused_body<2>(p); }
 
 // ------------------------------------------------ debug: one W tile via the main loop
 __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const FusedParams p, WTileJob job,
@@ -1023,6 +1083,8 @@ cudaError_t fused_configure(int* smem_bytes_out) {
   cudaError_t e = cudaFuncSetAttribute(pt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        FUSED_SMEM_BYTES);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pt_fused_kernel2, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_BYTES);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pt_w_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            FUSED_SMEM_BYTES);
   if (smem_bytes_out) *smem_bytes_out = FUSED_SMEM_BYTES;
@@ -1035,10 +1097,11 @@ cudaError_t launch_fused(const FusedParams& p, int grid, cudaStream_t s) {
     // the item-round barrier spins on other CTAs: co-residency must be guaranteed, not assumed
     FusedParams pc = p;
     void* args[] = {&pc};
-    return cudaLaunchCooperativeKernel((const void*)pt_fused_kernel, dim3(grid), dim3(FUSED_THREADS), args,
-                                       FUSED_SMEM_BYTES, s);
+    return cudaLaunchCooperativeKernel(p.t1b ? (const void*)pt_fused_kernel2 : (const void*)pt_fused_kernel, dim3(grid),
+                                       dim3(FUSED_THREADS), args, FUSED_SMEM_BYTES, s);
   }
-  pt_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(p);
+  if (p.t1b) pt_fused_kernel2<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(p);
+  else pt_fused_kernel<<<grid, FUSED_THREADS, FUSED_SMEM_BYTES, s>>>(p);
   return cudaGetLastError();
 }
 

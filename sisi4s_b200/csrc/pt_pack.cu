@@ -13,7 +13,7 @@ namespace pt {
 
 static inline unsigned blocks_for(size_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-// raw_slab[b + v*(c + v*d)] = Vppph[b,c,d,z]  ->  Vt slab [Q][R][dc][n][kk]
+// raw_slab[b + v*(c + v*d)] = Vppph[b,c,d,z], d < vd  ->  Vt slab [Q][R][dc][n][kk]
 __global__ void __launch_bounds__(256) pack_vt_slab_kernel(const double* __restrict__ raw,
                                                            double* __restrict__ vt, Dims d) {
   __shared__ double buf[4][256 + 8];
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) pack_vt_slab_kernel(const double* __restr
   for (int kk = 0; kk < 4; ++kk) {
     const int dd = 4 * dc + kk;
     double val = 0.0;
-    if (b < d.v && c < d.v && dd < d.v) val = raw[b + v * (c + v * dd)];
+    if (b < d.v && c < d.v && dd < d.vd) val = raw[b + v * (c + v * dd)];
     buf[kk][bl * 16 + cl] = val;
   }
   __syncthreads();
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) pack_vt_slab_kernel(const double* __restr
   }
 }
 
-// Tt[y][x][P][dc][m][kk] = T2[a=16P+m, d=4dc+kk, x, y]; one thread per (.., m) row
+// Tt[y][x][P][dc][m][kk] = T2[a=16P+m, d=4dc+kk, x, y] (raw [v,vd,o,o]); one thread per (.., m) row
 __global__ void __launch_bounds__(256) pack_tt_kernel(const double* __restrict__ t2,
                                                       double* __restrict__ tt, Dims d) {
   const size_t rows = (size_t)d.o * d.o * d.nr * d.nk4 * 16;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) pack_tt_kernel(const double* __restrict__
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const int dd = 4 * dc + kk;
-    out[kk] = (a < d.v && dd < d.v) ? t2[a + v * (dd + v * (x + (size_t)d.o * y))] : 0.0;
+    out[kk] = (a < d.v && dd < d.vd) ? t2[a + v * (dd + (size_t)d.vd * (x + (size_t)d.o * y))] : 0.0;
   }
   double2* dst = reinterpret_cast<double2*>(tt + gid * 4);
   dst[0] = make_double2(out[0], out[1]);

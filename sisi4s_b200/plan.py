@@ -324,3 +324,6 @@ def run_plan_file(path: str, data: dict | None = None, log=print) -> dict:
             for k, v in alg.log.items():
                 log(f"  {k}={v:.15g}")
     return data
+
+
+from . import triples_complex  # noqa: E402,F401  (registers CcsdPerturbativeTriplesComplex)

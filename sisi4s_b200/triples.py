@@ -57,7 +57,7 @@ class TriplesEngine:
 
     def __init__(self, o: int, v: int, device: int = 0, engine: int = _lib.PT_ENGINE_FUSED,
                  keep_raw: bool = False, grid: int = 0, slab_slots: int = 0, o_all: int | None = None,
-                 hole_block: int = 0, async_upload: bool = False, pin_host: bool = False):
+                 hole_block: int = 0, async_upload: bool = False, pin_host: bool = False, vd: int | None = None):
         """``o_all`` > ``o``: engine for a hole subset of a larger problem (pt_create_ex): ``o`` active
         holes (those of the triples that are run), ``o_all`` holes in the hole contraction.
         ``hole_block`` = b: out-of-core mode of the library (BASELINE configs[4]): the setters take the
@@ -69,6 +69,10 @@ class TriplesEngine:
         self._h = C.c_void_p()
         _lib.check(self.lib.pt_create_ex(C.byref(self._h), self.o, self.o_all, self.v, int(device)))
         self._keepalive = []
+        # vd: length of the particle contraction when it differs from v (stacked complex problem)
+        self.vd = self.v if vd is None else int(vd)
+        if self.vd != self.v:
+            self.set_option("particle_contraction", self.vd)
         self.hole_block = int(hole_block)
         if hole_block:
             self.set_option("hole_block", int(hole_block))   # first: it re-dimensions the device buffers
@@ -134,8 +138,15 @@ class TriplesEngine:
 
     def set_doubles(self, t2):
         t2 = self._hold(_f64(t2))
-        self._shape(t2, (self.v, self.v, self.o, self.o), "CcsdDoublesAmplitudes")
+        self._shape(t2, (self.v, self.vd, self.o, self.o), "CcsdDoublesAmplitudes")
         _lib.check(self.lib.pt_set_doubles(self._h, _ptr(t2)))
+
+    def set_singles_pair(self, t1b, vabij_b):
+        """Second singles term S += 1/2 t1b (x) vabij_b (complex triples)."""
+        t1b, vabij_b = self._hold(_f64(t1b)), self._hold(_f64(vabij_b))
+        self._shape(t1b, (self.v, self.o), "CcsdSinglesAmplitudes (second term)")
+        self._shape(vabij_b, (self.v, self.v, self.o, self.o), "PPHHCoulombIntegrals (second term)")
+        _lib.check(self.lib.pt_set_singles_pair(self._h, _ptr(t1b), _ptr(vabij_b)))
 
     def set_doubles_hole(self, t2_xl):
         """Hole-term doubles T2[a,b,x,l], x active / l all holes (pt_create_ex engines only)."""
@@ -155,11 +166,11 @@ class TriplesEngine:
 
     def set_ppph(self, vabci, slabs_per_call: int = 0):
         vabci = self._hold(_f64(vabci))
-        self._shape(vabci, (self.v, self.v, self.v, self.o), "PPPHCoulombIntegrals")
+        self._shape(vabci, (self.v, self.v, self.vd, self.o), "PPPHCoulombIntegrals")
         if self.hole_block:
             return self.set_ppph_host(vabci)
         step = slabs_per_call or self.o
-        slab = self.v ** 3
+        slab = self.v * self.v * self.vd
         flat = vabci.reshape(-1, order="F")
         for k0 in range(0, self.o, step):
             k1 = min(self.o, k0 + step)
@@ -170,7 +181,7 @@ class TriplesEngine:
         """PPPHCoulombIntegrals kept in host memory; with ``slab_slots`` the engine uploads
         slabs on demand, so the array is kept alive by this object."""
         vabci = _f64(vabci)
-        self._shape(vabci, (self.v, self.v, self.v, self.o), "PPPHCoulombIntegrals")
+        self._shape(vabci, (self.v, self.v, self.vd, self.o), "PPPHCoulombIntegrals")
         self._keepalive.append(vabci)
         _lib.check(self.lib.pt_set_ppph_host(self._h, _ptr(vabci)))
 
