@@ -5,10 +5,11 @@ HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CHILD = r'''
 import json, os, sys
 sys.path.insert(0, %r)
-from sisi4s_b200 import synthetic as S
+import torch
+import bench
 from sisi4s_b200.triples import TriplesEngine
 dbg = [x for x in sys.argv[1].split(",")]
-inp = S.make_inputs(40, 300, seed=2026, kind="vertex", nf=24)
+inp = bench.generate_inputs(bench.WORKLOADS["o40v300"], torch.device("cuda", 0), bench.HostBuffers(False, 0, lambda: None, "ab"), 0, 1)
 with TriplesEngine(40, 300) as eng:
     eng.set_inputs(*inp.args())
     b, e = eng.partition(8, 3)

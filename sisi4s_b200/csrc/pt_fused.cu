@@ -368,15 +368,15 @@ struct Consumer {
     probe();
   }
   // load n of the next unit (K = particle chunk half 0/1, hole half-chunk 0/1)
-  template <int NEXT, int N>
+  template <int NEXT, int N, int NB = 4>
   __device__ __forceinline__ void ld(FragP& fp, FragH& fh, double (&u)[2]) {
     if constexpr (NEXT == NEXT_P0 || NEXT == NEXT_P1) {
       constexpr int C = (NEXT == NEXT_P1) ? 1 : 0;
-      if constexpr (N < 8) fp.b[N >> 1][N & 1] = lds_f64<C * 8192 + (N >> 1) * 2048 + (N & 1) * 256>(B);
+      if constexpr (N < 8) { if constexpr ((N >> 1) < NB) fp.b[N >> 1][N & 1] = lds_f64<C * 8192 + (N >> 1) * 2048 + (N & 1) * 256>(B); }
       else if constexpr (N < 10) fp.a[N - 8] = lds_f64<C * 512 + (N - 8) * 256>(A);
     } else if constexpr (NEXT == NEXT_H0 || NEXT == NEXT_H1) {
       constexpr int G = (NEXT == NEXT_H1) ? 1 : 0;
-      if constexpr (N < 4) fh.a[N >> 1][N & 1] = lds_f64<G * 4096 + (N >> 1) * 2048 + (N & 1) * 256>(H);
+      if constexpr (N < 4) { if constexpr (2 * G + (N >> 1) < NB) fh.a[N >> 1][N & 1] = lds_f64<G * 4096 + (N >> 1) * 2048 + (N & 1) * 256>(H); }
       else if constexpr (N < 6 && NEXT == NEXT_H0) u[N - 4] = lds_f64<(N - 4) * 256>(A);
     }
   }
@@ -385,52 +385,57 @@ struct Consumer {
     return (NEXT == NEXT_P0 || NEXT == NEXT_P1) ? 10 : (NEXT == NEXT_H0 ? 6 : (NEXT == NEXT_H1 ? 4 : 0));
   }
 
-  // 16 DMMAs of particle chunk `cur`, with the next unit fetched in between
-  template <int NEXT>
+  // 16 DMMAs of particle chunk `cur`, with the next unit fetched in between.  NB < 4: the step's b range is
+  // the padded last particle range and only its first NB column groups (b = wq + 4 bi, bi < NB) hold
+  // valid particles; the DMMAs and fragment loads of the others are not issued (their accumulators stay 0).
+  template <int NEXT, int NB>
   __device__ __forceinline__ void block_p(double (&acc)[2][4][2][2], const FragP& cur, FragP& fp, FragH& fh,
                                           double (&u)[2], bool last) {
     constexpr int NL = nloads<NEXT>();
     constexpr bool first = (NEXT == NEXT_P0 || NEXT == NEXT_H0);
-#define PT_DM(n) dmma(acc[(n) >> 3][((n) >> 1) & 3][(n) & 1][0], acc[(n) >> 3][((n) >> 1) & 3][(n) & 1][1], \
-                      cur.a[(n) >> 3], cur.b[((n) >> 1) & 3][(n) & 1])
+#define PT_DM(n) do { if constexpr ((((n) >> 1) & 3) < NB)                                                      \
+      dmma(acc[(n) >> 3][((n) >> 1) & 3][(n) & 1][0], acc[(n) >> 3][((n) >> 1) & 3][(n) & 1][1],               \
+           cur.a[(n) >> 3], cur.b[((n) >> 1) & 3][(n) & 1]); } while (0)
     PT_DM(0);
     if constexpr (first) await();
-    ld<NEXT, 0>(fp, fh, u); PT_DM(1);
-    ld<NEXT, 1>(fp, fh, u); PT_DM(2);
-    ld<NEXT, 2>(fp, fh, u); PT_DM(3);
-    ld<NEXT, 3>(fp, fh, u); PT_DM(4);
-    ld<NEXT, 4>(fp, fh, u); PT_DM(5);
-    ld<NEXT, 5>(fp, fh, u); PT_DM(6);
-    ld<NEXT, 6>(fp, fh, u); PT_DM(7);
-    ld<NEXT, 7>(fp, fh, u); PT_DM(8);
-    ld<NEXT, 8>(fp, fh, u); PT_DM(9);
-    ld<NEXT, 9>(fp, fh, u); PT_DM(10);
+    ld<NEXT, 0, NB>(fp, fh, u); PT_DM(1);
+    ld<NEXT, 1, NB>(fp, fh, u); PT_DM(2);
+    ld<NEXT, 2, NB>(fp, fh, u); PT_DM(3);
+    ld<NEXT, 3, NB>(fp, fh, u); PT_DM(4);
+    ld<NEXT, 4, NB>(fp, fh, u); PT_DM(5);
+    ld<NEXT, 5, NB>(fp, fh, u); PT_DM(6);
+    ld<NEXT, 6, NB>(fp, fh, u); PT_DM(7);
+    ld<NEXT, 7, NB>(fp, fh, u); PT_DM(8);
+    ld<NEXT, 8, NB>(fp, fh, u); PT_DM(9);
+    ld<NEXT, 9, NB>(fp, fh, u); PT_DM(10);
     if (NL > 0 && last) release();
     PT_DM(11); PT_DM(12); PT_DM(13); PT_DM(14); PT_DM(15);
 #undef PT_DM
   }
   // 8 DMMAs of hole half-chunk g (columns bi = 2g + j)
-  template <int NEXT, int G>
+  template <int NEXT, int G, int NB>
   __device__ __forceinline__ void block_h(double (&acc)[2][4][2][2], const FragH& cur, const double (&uc)[2],
                                           FragP& fp, FragH& fh, double (&u)[2]) {
     constexpr bool first = (NEXT == NEXT_H0);
-#define PT_DH(n) dmma(acc[(n) & 1][2 * G + ((n) >> 2)][((n) >> 1) & 1][0],                      \
-                      acc[(n) & 1][2 * G + ((n) >> 2)][((n) >> 1) & 1][1], cur.a[(n) >> 2][(n) & 1], \
-                      uc[((n) >> 1) & 1])
+#define PT_DH(n) do { if constexpr (2 * G + ((n) >> 2) < NB)                                               \
+      dmma(acc[(n) & 1][2 * G + ((n) >> 2)][((n) >> 1) & 1][0],                                            \
+           acc[(n) & 1][2 * G + ((n) >> 2)][((n) >> 1) & 1][1], cur.a[(n) >> 2][(n) & 1],                  \
+           uc[((n) >> 1) & 1]); } while (0)
     PT_DH(0);
     if constexpr (first) await();
-    ld<NEXT, 0>(fp, fh, u); PT_DH(1);
-    ld<NEXT, 1>(fp, fh, u); PT_DH(2);
-    ld<NEXT, 2>(fp, fh, u); PT_DH(3);
-    ld<NEXT, 3>(fp, fh, u); PT_DH(4);
-    ld<NEXT, 4>(fp, fh, u); PT_DH(5);
-    ld<NEXT, 5>(fp, fh, u);
+    ld<NEXT, 0, NB>(fp, fh, u); PT_DH(1);
+    ld<NEXT, 1, NB>(fp, fh, u); PT_DH(2);
+    ld<NEXT, 2, NB>(fp, fh, u); PT_DH(3);
+    ld<NEXT, 3, NB>(fp, fh, u); PT_DH(4);
+    ld<NEXT, 4, NB>(fp, fh, u); PT_DH(5);
+    ld<NEXT, 5, NB>(fp, fh, u);
     if constexpr (NEXT == NEXT_H1) release();
     PT_DH(6); PT_DH(7);
 #undef PT_DH
   }
 };
 
+template <int NB>
 __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], Pipe& pp, int nk4, int nl4, int en,
                                              int h, int wq, int lane) {
 #pragma unroll
@@ -477,42 +482,42 @@ __device__ __forceinline__ void consume_step(double (&acc)[2][4][2][2], Pipe& pp
   for (; dc + 9 < nk4; dc += 8) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      c.block_p<NEXT_P1>(acc, fA, fB, hB, un, true);    // chunk dc+2r;   fetch dc+2r+1, stage done
-      c.block_p<NEXT_P0>(acc, fB, fA, hA, uf, false);   // chunk dc+2r+1; fetch dc+2r+2 (dc+2r+3 exists)
+      c.block_p<NEXT_P1, NB>(acc, fA, fB, hB, un, true);    // chunk dc+2r;   fetch dc+2r+1, stage done
+      c.block_p<NEXT_P0, NB>(acc, fB, fA, hA, uf, false);   // chunk dc+2r+1; fetch dc+2r+2 (dc+2r+3 exists)
     }
   }
   for (; dc + 5 < nk4; dc += 4) {
-    c.block_p<NEXT_P1>(acc, fA, fB, hB, un, true);    // chunk dc;   fetch dc+1, stage done
-    c.block_p<NEXT_P0>(acc, fB, fA, hA, uf, false);   // chunk dc+1; fetch dc+2
-    c.block_p<NEXT_P1>(acc, fA, fB, hB, un, true);    // chunk dc+2; fetch dc+3, stage done
-    c.block_p<NEXT_P0>(acc, fB, fA, hA, uf, false);   // chunk dc+3; fetch dc+4 (dc+5 exists)
+    c.block_p<NEXT_P1, NB>(acc, fA, fB, hB, un, true);    // chunk dc;   fetch dc+1, stage done
+    c.block_p<NEXT_P0, NB>(acc, fB, fA, hA, uf, false);   // chunk dc+1; fetch dc+2
+    c.block_p<NEXT_P1, NB>(acc, fA, fB, hB, un, true);    // chunk dc+2; fetch dc+3, stage done
+    c.block_p<NEXT_P0, NB>(acc, fB, fA, hA, uf, false);   // chunk dc+3; fetch dc+4 (dc+5 exists)
   }
   for (; dc + 1 < nk4; dc += 2) {
-    c.block_p<NEXT_P1>(acc, fA, fB, hB, un, true);                      // chunk dc; fetch dc+1, stage done
-    if (dc + 2 < nk4) c.block_p<NEXT_P0>(acc, fB, fA, hA, uf, dc + 3 >= nk4);  // chunk dc+1; fetch dc+2
-    else c.block_p<NEXT_H0>(acc, fB, fA, hA, uf, false);                // chunk dc+1; fetch hole (0, g=0)
+    c.block_p<NEXT_P1, NB>(acc, fA, fB, hB, un, true);                      // chunk dc; fetch dc+1, stage done
+    if (dc + 2 < nk4) c.block_p<NEXT_P0, NB>(acc, fB, fA, hA, uf, dc + 3 >= nk4);  // chunk dc+1; fetch dc+2
+    else c.block_p<NEXT_H0, NB>(acc, fB, fA, hA, uf, false);                // chunk dc+1; fetch hole (0, g=0)
   }
-  if (nk4 & 1) c.block_p<NEXT_H0>(acc, fA, fB, hA, uf, false);          // tail chunk; fetch hole (0, g=0)
+  if (nk4 & 1) c.block_p<NEXT_H0, NB>(acc, fA, fB, hA, uf, false);          // tail chunk; fetch hole (0, g=0)
   // ---- hole contraction: W[a,b,c] += sum_l T2[a,b,x,l] (-Vhhhp[y,z,l,c]); half-chunk g covers
   //      b = 8g .. 8g+7, of which this warp owns b = 8g + wq + 4j  (bi = 2g + j)
   int lc = 0;
   for (; lc + 4 < nl4; lc += 4) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      c.block_h<NEXT_H1, 0>(acc, hA, uf, fA, hB, un);
-      c.block_h<NEXT_H0, 1>(acc, hB, uf, fA, hA, un);
+      c.block_h<NEXT_H1, 0, NB>(acc, hA, uf, fA, hB, un);
+      c.block_h<NEXT_H0, 1, NB>(acc, hB, uf, fA, hA, un);
       uf[0] = un[0];
       uf[1] = un[1];
     }
   }
   for (; lc + 1 < nl4; ++lc) {
-    c.block_h<NEXT_H1, 0>(acc, hA, uf, fA, hB, un);
-    c.block_h<NEXT_H0, 1>(acc, hB, uf, fA, hA, un);
+    c.block_h<NEXT_H1, 0, NB>(acc, hA, uf, fA, hB, un);
+    c.block_h<NEXT_H0, 1, NB>(acc, hB, uf, fA, hA, un);
     uf[0] = un[0];
     uf[1] = un[1];
   }
-  c.block_h<NEXT_H1, 0>(acc, hA, uf, fA, hB, un);
-  c.block_h<NEXT_NONE, 1>(acc, hB, uf, fA, hA, un);
+  c.block_h<NEXT_H1, 0, NB>(acc, hA, uf, fA, hB, un);
+  c.block_h<NEXT_NONE, 1, NB>(acc, hB, uf, fA, hA, un);
 }
 
 // composition table of Permutation<3> indices: S3_MUL[mu][nu] = index of m -> mu(nu(m)), i.e.
@@ -751,7 +756,13 @@ __device__ __forceinline__ void fused_body(const FusedParams& p) {
       const PtStep& st = tab.steps[s];
       const PtHalf& hf = st.h[grp];
       double acc[2][4][2][2];
-      consume_step(acc, pp, nk4, nl4, (p.debug & 1) ? 0 : hf.en, grp, wq, lane);
+#ifdef PT_SKIP_PADDED_B
+      // the step's b range (r1) is the padded last particle range with <= 12 valid particles: skip column group 3
+      if (sel3(ob.x, ob.y, ob.z, st.r1) == p.d.nr - 1 && p.d.v - TILE * (p.d.nr - 1) <= 12)
+        consume_step<3>(acc, pp, nk4, nl4, (p.debug & 1) ? 0 : hf.en, grp, wq, lane);
+      else
+#endif
+      consume_step<4>(acc, pp, nk4, nl4, (p.debug & 1) ? 0 : hf.en, grp, wq, lane);
       // the halves of a step target different X tiles except in orbits with coinciding
       // ranges; only then (or for very short steps) are the two scatters separated by barriers
       const bool sync = step_sync_always || (st.h[0].en && st.h[1].en && st.h[0].tau == st.h[1].tau);
@@ -1063,7 +1074,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1) pt_w_tile_kernel(const Fused
   }
   const int grp = warp >> 2, wq = warp & 3;
   double acc[2][4][2][2];
-  consume_step(acc, pp, p.d.nk4, p.d.nl4, grp == 0, grp, wq, lane);
+  consume_step<4>(acc, pp, p.d.nk4, p.d.nl4, grp == 0, grp, wq, lane);
   if (grp != 0) return;
 #pragma unroll
   for (int mf = 0; mf < 2; ++mf)

@@ -50,8 +50,12 @@ def test_o64_v512_sampled_triples_match_c_oracle():
     """BASELINE configs[3] shape (105 GB resident, PPPH built on the device from the vertex): sampled
     triples vs the C oracle, which is handed only the PPPH slabs of the sampled triples."""
     from oracle import c_oracle as CO
+    import torch
+    from sisi4s_b200.synthetic_device import HostBuffers, generate_inputs
     o, v = 64, 512
-    inp = S.make_inputs(o, v, seed=2026, kind="vertex", nf=24, with_ppph=False)
+    # inputs generated on the device (minutes of NumPy otherwise); the oracle reads the same host arrays
+    host = HostBuffers(False, 0, lambda: None, "test")
+    inp = generate_inputs(dict(o=o, v=v, mode="resident", ppph_host=False), torch.device("cuda", 0), host, 0, 1)
     tr = _triples(o)
     trip = ((3, 17, 40), (5, 5, 30), (7, 21, 21))
     picks = [tr.index(t) for t in trip]
