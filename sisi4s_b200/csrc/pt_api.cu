@@ -101,8 +101,6 @@ struct PtHandle_ {
   // only those its triples touch, on a second stream while earlier waves of triples already compute
   bool lazy_ppph = false;
   cudaStream_t copy_stream = nullptr;
-  double* wave_stage = nullptr;  // raw slabs in flight
-  size_t cap_wave = 0;
   // hole-block mode (option hole_block = b: BASELINE configs[4]): T2 / PPHH stay in caller-owned host
   // memory, the sorted triples are walked by hole-block triples (I<=J<=K), each group's <= 3b active
   // holes are staged into the buffers above (sized for 3b holes once) before its launch
@@ -417,7 +415,6 @@ int pt_destroy(pt_handle_t h) {
   if (h->d_sync) cudaFree(h->d_sync);
   if (h->d_list) cudaFree(h->d_list);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-  if (h->wave_stage) cudaFree(h->wave_stage);
   for (void* p : h->registered) cudaHostUnregister(p);
   for (cudaEvent_t ev : {h->ev0, h->ev1, h->ev_up0, h->ev_up1})
     if (ev) cudaEventDestroy(ev);
@@ -689,7 +686,7 @@ int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
   if (!h || !vabci) return fail(PT_ERR_INVALID, "pt_set_ppph_host: null");
   if (!h->blocked() && !(h->async_upload && !h->keep_raw && !h->hole_block)) return pt_set_ppph_slabs(h, 0, h->oh(), vabci);
   CU(cudaSetDevice(h->device));
-  RC(ensure_ppph_buffers(h, h->blocked()));
+  RC(ensure_ppph_buffers(h, true));
   h->lazy_ppph = !h->blocked();   // everything fits: pt_run uploads the slabs its triples touch, in waves
   h->host_ppph = vabci;
   pin(h, vabci, (size_t)h->d.v * h->d.v * h->d.vd * h->oh());
@@ -1127,11 +1124,17 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
       struct WevGuard { std::vector<cudaEvent_t>& v; ~WevGuard() { for (auto e : v) if (e) cudaEventDestroy(e); } } wevguard{wev};
       size_t waves_issued = 0;
       const size_t slab3 = (size_t)h->d.v * h->d.v * h->d.vd;
+      // raw slab q waits for its packing in the (still empty) slot of the NEXT missing slab -- a packed slab
+      // is never smaller than a raw one, and slot missing[q+1] is written only by pack(q+1), after pack(q)
+      // has read it -- the last one in the one-slab staging buffer: no extra device memory
+      auto raw_home = [&](size_t q) -> double* {
+        return q + 1 < missing.size() ? h->Vt + vt_slab_elems(h->d) * (size_t)missing[q + 1] : h->slab_stage;
+      };
       auto issue_waves = [&](size_t upto) -> int {   // enqueue the copies of all waves < upto
         for (; waves_issued < std::min(upto, wave_end.size()); ++waves_issued) {
           const size_t w = waves_issued;
           for (size_t q = w ? wave_end[w - 1] : 0; q < (size_t)wave_end[w]; ++q) {
-            CU(cudaMemcpyAsync(h->wave_stage + slab3 * q, h->host_ppph + slab3 * (size_t)missing[q], slab3 * sizeof(double),
+            CU(cudaMemcpyAsync(raw_home(q), h->host_ppph + slab3 * (size_t)missing[q], slab3 * sizeof(double),
                                cudaMemcpyHostToDevice, h->copy_stream));
             h->stats.bytes_h2d += (double)(slab3 * sizeof(double));
           }
@@ -1142,7 +1145,10 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
       };
       if (!missing.empty()) {
         if (!h->copy_stream) CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        CU(h->grow(&h->wave_stage, &h->cap_wave, slab3 * missing.size()));
+        // the copy stream must not overtake earlier work of the compute stream that still reads these areas
+        // (the previous run's last pack out of slab_stage)
+        CU(cudaEventRecord(h->ev1, h->stream));
+        CU(cudaStreamWaitEvent(h->copy_stream, h->ev1, 0));
         RC(issue_waves(1));
       }
       std::vector<cudaEvent_t> kev(2 * groups.size(), nullptr);
@@ -1163,7 +1169,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
             if (!wev[ww]) continue;
             CU(cudaStreamWaitEvent(h->stream, wev[ww], 0));
             for (int q = ww ? wave_end[ww - 1] : 0; q < wave_end[ww]; ++q)
-              RC(pack_into_slot(h, h->wave_stage + slab3 * (size_t)q, missing[q], missing[q]));
+              RC(pack_into_slot(h, raw_home((size_t)q), missing[q], missing[q]));
             h->stats.slab_loads += wave_end[ww] - (ww ? wave_end[ww - 1] : 0);
             CU(cudaEventDestroy(wev[ww]));
             wev[ww] = nullptr;
