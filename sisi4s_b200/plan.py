@@ -326,4 +326,4 @@ def run_plan_file(path: str, data: dict | None = None, log=print) -> dict:
     return data
 
 
-from . import triples_complex  # noqa: E402,F401  (registers CcsdPerturbativeTriplesComplex)
+from . import triples_complex, triples_spin_orbital  # noqa: E402,F401  (register CcsdPerturbativeTriplesComplex, UPerturbativeTriples)
