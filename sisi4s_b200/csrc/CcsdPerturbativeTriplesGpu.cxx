@@ -143,6 +143,8 @@ void CcsdPerturbativeTriplesGpu::run() {
   const int64_t slabSlots(getIntegerArgument("slabSlots", 0));
   if (holeBlock > 0) PT_CHECK(pt_set_option(h, "hole_block", holeBlock));   // first: re-dimensions the buffers
   if (slabSlots > 0) PT_CHECK(pt_set_option(h, "slab_slots", slabSlots));
+  // pinHost (default on with holeBlock): page-lock the gathered host copies the library streams blocks from
+  if (getIntegerArgument("pinHost", holeBlock > 0 ? 1 : 0) != 0) PT_CHECK(pt_set_option(h, "pin_host", 1));
   const bool blocked((holeBlock > 0) || (slabSlots > 0 && slabSlots < No));
   // host copies the library reads on demand in the blocked modes: they must outlive pt_run
   std::vector<double> hostT2, hostPphh, hostPpph;

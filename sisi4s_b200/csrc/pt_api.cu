@@ -112,6 +112,7 @@ struct PtHandle_ {
   std::vector<int> cur_holes;    // holes currently staged
   std::vector<void*> registered; // cudaHostRegister'ed caller buffers
   bool pphh_from_vertex = false, hhhp_from_vertex = false;
+  bool ppph_from_vertex = false;   // slabs come from the resident vertex (pt_set_vertex was the last PPPH source given)
   // holes of the triple enumeration = holes that own a PPPH slab: the active holes of the engine, or --
   // in hole-block mode, where the active set changes from group to group -- all holes of the problem
   int oh() const { return hole_block ? o_full : d.o; }
@@ -670,6 +671,7 @@ int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
                                 "use pt_set_ppph_host or pt_set_vertex");
   CU(cudaSetDevice(h->device));
   RC(ensure_ppph_buffers(h, true));
+  h->ppph_from_vertex = false;
   UploadScope up(h);
   const size_t slab = (size_t)h->d.v * h->d.v * h->d.vd;
   for (int k = k0; k < k1; ++k) {
@@ -689,6 +691,7 @@ int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
   RC(ensure_ppph_buffers(h, true));
   h->lazy_ppph = !h->blocked();   // everything fits: pt_run uploads the slabs its triples touch, in waves
   h->host_ppph = vabci;
+  h->ppph_from_vertex = false;    // a vertex given earlier stays resident (PPHH / HHHP may come from it) but no longer feeds the slabs
   pin(h, vabci, (size_t)h->d.v * h->d.v * h->d.vd * h->oh());
   std::fill(h->slab_set.begin(), h->slab_set.end(), 1);
   std::fill(h->slot_of.begin(), h->slot_of.end(), -1);
@@ -724,6 +727,7 @@ int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double
     h->stats.kernel_launches += 1;
   }
   h->host_ppph = nullptr;   // the vertex is the PPPH source from now on
+  h->ppph_from_vertex = true;
   std::fill(h->slab_set.begin(), h->slab_set.end(), 1);
   std::fill(h->slot_of.begin(), h->slot_of.end(), -1);
   std::fill(h->hole_in.begin(), h->hole_in.end(), -1);
@@ -830,7 +834,7 @@ static int ensure_slabs(pt_handle_t h, const std::vector<int>& need) {
       if (victim < 0 || h->slot_tick[s] < h->slot_tick[victim]) victim = s;
     }
     if (victim < 0) return fail(PT_ERR_INVALID, "ensure_slabs: %zu slabs needed, %d slots", need.size(), h->nslots());
-    if (h->gp) {
+    if (h->gp && h->ppph_from_vertex) {
       RC(build_slab_packed(h, z, h->Vt + vt_slab_elems(h->d) * (size_t)victim));
       note_slot(h, z, victim);
     } else if (h->host_ppph) {

@@ -142,6 +142,12 @@ constexpr int TMEM_COLS = 512;
 #define PT_CONSUMER_REGS 224
 #define PT_PRODUCER_REGS 56
 #endif
+// unroll factor of the epilogue's x2 point loops (16 = full; experiment: smaller bodies against the
+// instruction-cache misses ncu shows there)
+#ifndef PT_EPI_UNROLL
+#define PT_EPI_UNROLL 16
+#endif
+constexpr int EPI_UNROLL = PT_EPI_UNROLL;
 constexpr int CONSUMER_REGS = PT_CONSUMER_REGS;
 constexpr int PRODUCER_REGS = PT_PRODUCER_REGS;
 static_assert(NCONSUMER_WARPS * 32 * CONSUMER_REGS + NPRODUCER_WARPS * 32 * PRODUCER_REGS <= 65536, "register file");
@@ -866,7 +872,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p) {
         double* R4 = Xs + 4 * XT_DBL + 16 * x0 + 256 * x1;
         double* R5 = Xs + 5 * XT_DBL + 16 * x1 + 256 * x0;
         const double cf[6] = {c0, c1, c2, c3, c4, c5};
-#pragma unroll
+#pragma unroll EPI_UNROLL
         for (int x2 = 0; x2 < 16; ++x2) {
           const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
           double* A[6] = {R0 + a01 + 256 * x2, R1 + a01 + 256 * x2, R2 + a25 + 16 * x2,
@@ -904,7 +910,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p) {
         const double* Q0 = Qc + x1;
         const double* Q1 = Qc + 256 + x0;
         const double* P0 = Xs + tl * XT_DBL + 16 * x1;
-#pragma unroll
+#pragma unroll EPI_UNROLL
         for (int x2 = 0; x2 < 16; ++x2) {
           const int a01 = l01 ^ bitswap13(x2);
           const double sd = t0 * Q0[16 * x2] + t1v * Q1[16 * x2] + tc[32 + x2] * q2c;
@@ -963,7 +969,7 @@ __device__ __forceinline__ void fused_body(const FusedParams& p) {
         const double* P3 = Xs + nb[3] * XT_DBL + 256 * x1;
         const double* P4 = Xs + nb[4] * XT_DBL + 16 * x0 + 256 * x1;
         const double* P5 = Xs + nb[5] * XT_DBL + 16 * x1 + 256 * x0;
-#pragma unroll
+#pragma unroll EPI_UNROLL
         for (int x2 = 0; x2 < 16; ++x2) {
           // nu = Permutation<3>(n): (x o nu)_m = x_{nu(m)}; nbr[tl][0] == tl (identity)
           const int a01 = l01 ^ bitswap13(x2), a25 = l25 ^ x2, a34 = l34 ^ x2;
