@@ -204,8 +204,8 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 
 }  // namespace
 
-constexpr int VG_BM = 64, VG_BN = 128, VG_STAGES = 4;
-constexpr int VG_STAGE_DBL = (VG_BM + VG_BN) * 16;                      // K = 16 per stage: 24 KB
+constexpr int VG_BM = 64, VG_BN = 128, VG_STAGES = 4;                   // VG_BN: the wide N tile; BN = 64 variant below
+constexpr int VG_STAGE_DBL = (VG_BM + VG_BN) * 16;                      // K = 16 per stage: 24 KB (sized for BN = 128)
 constexpr int VG_THREADS = 9 * 32;                                      // 8 consumer warps + 1 producer warp
 constexpr int VG_SMEM_BYTES = VG_STAGES * VG_STAGE_DBL * 8 + 2 * VG_STAGES * 8;
 
@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(256) pack_vertex_kernel(const double* __restri
   dst[1] = make_double2(out[2], out[3]);
 }
 
-template <int MODE>
+// BN = 128: warp tile 32 x 32 (4 x 4 DMMA); BN = 64: warp tile 32 x 16 (4 x 2) for N extents that would waste
+// more than 10 % of a 128-wide tiling (v = 300: 384 vs 320 columns).
+template <int MODE, int BN>
 __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgParams p) {
+  constexpr int NJ = BN / 32;   // 8-column DMMA fragments per warp
   extern __shared__ __align__(128) unsigned char vg_smem[];
   double* ring = reinterpret_cast<double*>(vg_smem);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + VG_STAGES * VG_STAGE_DBL);
@@ -263,12 +266,12 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
     dc = mt - Q * p.nk4;
     const int d = min(4 * dc + g_, p.v - 1);                     // padded d: clamped source, masked output
     rowA = p.a_base + 16 * Q + (long long)p.np * (p.a0 + d);     // rows (b, d): G[., a0 + b, a0 + d]
-    rowB = p.b_base + (long long)VG_BN * nt;                     // rows (c, z): G[., a0 + c, z]
+    rowB = p.b_base + (long long)BN * nt;                        // rows (c, z): G[., a0 + c, z]
   } else {
     const int b0 = batch % p.nb0, b1 = batch / p.nb0;
     const long long s0 = p.map0 ? p.map0[b0] : b0, s1 = p.map1 ? p.map1[b1] : b1;
     rowA = p.a_base + p.a_s0 * s0 + p.a_s1 * s1 + (long long)VG_BM * mt + 16 * g_;
-    rowB = p.b_base + p.b_s0 * s0 + p.b_s1 * s1 + (long long)VG_BN * nt;
+    rowB = p.b_base + p.b_s0 * s0 + p.b_s1 * s1 + (long long)BN * nt;
     outoff = p.o_s0 * b0 + p.o_s1 * b1;
   }
   const int nstage = (p.kp4 + 3) >> 2;   // kp4 is a multiple of 4 (K padded to 16)
@@ -278,15 +281,15 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
     const bool isA = lane < 16, act = lane < 20;
     const int kcl = isA ? (lane >> 2) : (lane - 16);
     const long long row = isA ? rowA : rowB;
-    const uint32_t bytes = isA ? 512u : 4096u;
-    const uint32_t soff = isA ? (uint32_t)((kcl * VG_BM + 16 * (lane & 3)) * 32) : (uint32_t)(VG_BM * 128 + kcl * VG_BN * 32);
+    const uint32_t bytes = isA ? 512u : (uint32_t)(BN * 32);
+    const uint32_t soff = isA ? (uint32_t)((kcl * VG_BM + 16 * (lane & 3)) * 32) : (uint32_t)(VG_BM * 128 + kcl * BN * 32);
     const double* src = ((isA || !p.gpb) ? p.gp : p.gpb) + (size_t)row * 4;
     const size_t kstride = (size_t)((isA || !p.gpb) ? p.rows_padded : p.rows_padded_b) * 4;   // doubles per K chunk of 4
     for (int s = 0; s < nstage; ++s) {
       const int slot = s % VG_STAGES;
       const uint32_t ph = (uint32_t)(s / VG_STAGES) & 1u;
       vg_mbar_wait(empty_u + 8 * slot, ph ^ 1u);
-      if (lane == 0) vg_mbar_expect_tx(full_u + 8 * slot, (uint32_t)(VG_STAGE_DBL * 8));
+      if (lane == 0) vg_mbar_expect_tx(full_u + 8 * slot, (uint32_t)((VG_BM + BN) * 16 * 8));
       __syncwarp();
       if (act)
         vg_bulk_g2s(ring_u + slot * (VG_STAGE_DBL * 8) + soff, src + (size_t)(4 * s + kcl) * kstride, bytes, full_u + 8 * slot);
@@ -296,28 +299,28 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
 
   // ===== consumer warps: warp tile 32 x 32
   const int wm = warp & 1, wn = warp >> 1;
-  double acc[4][4][2];
+  double acc[4][NJ][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int s = 0; s < nstage; ++s) {
     const int slot = s % VG_STAGES;
     const uint32_t ph = (uint32_t)(s / VG_STAGES) & 1u;
     vg_mbar_wait(full_u + 8 * slot, ph);
     const double* As = ring + slot * VG_STAGE_DBL + 32 * wm * 4 + lane;
-    const double* Bs = ring + slot * VG_STAGE_DBL + VG_BM * 16 + 32 * wn * 4 + lane;
+    const double* Bs = ring + slot * VG_STAGE_DBL + VG_BM * 16 + 8 * NJ * wn * 4 + lane;
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) {
-      double af[4], bf[4];
+      double af[4], bf[NJ];
 #pragma unroll
       for (int i = 0; i < 4; ++i) af[i] = As[kc * VG_BM * 4 + 32 * i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) bf[j] = Bs[kc * VG_BN * 4 + 32 * j];
+      for (int j = 0; j < NJ; ++j) bf[j] = Bs[kc * BN * 4 + 32 * j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < NJ; ++j) dmma_884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
     __syncwarp();
     if (lane == 0) vg_mbar_arrive(empty_u + 8 * slot);
@@ -332,10 +335,10 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
       const int m = 32 * wm + 8 * i + g, kk = m >> 4, bl = m & 15;
       const bool mok = (16 * Q + bl < p.v) && (4 * dc + kk < p.v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int c = VG_BN * nt + 32 * wn + 8 * j + t2 + e;
+          const int c = BN * nt + 8 * NJ * wn + 8 * j + t2 + e;
           const int R = c >> 4, cl = c & 15;
           if (R < p.nr)
             p.out[((size_t)(Q * p.nr + R) * p.nk4 + dc) * 1024 + (size_t)(16 * bl + cl) * 4 + kk] =
@@ -348,10 +351,10 @@ __global__ void __launch_bounds__(VG_THREADS, 2) vertex_gemm_kernel(const VgPara
       const int m = VG_BM * mt + 32 * wm + 8 * i + g;
       if (m >= p.M) continue;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NJ; ++j)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int n = VG_BN * nt + 32 * wn + 8 * j + t2 + e;
+          const int n = BN * nt + 8 * NJ * wn + 8 * j + t2 + e;
           if (n < p.N) {
             double* o = p.out + outoff + (long long)m * p.sm + (long long)n * p.sn;
             *o = p.accumulate ? p.alpha * acc[i][j][e] + p.beta * *o : p.alpha * acc[i][j][e];
@@ -405,10 +408,12 @@ cudaError_t launch_pphh_symsum(const double* pphh, double* qsum, Dims d, cudaStr
   return cudaGetLastError();
 }
 cudaError_t vertex_gemm_configure() {
-  cudaError_t e = cudaFuncSetAttribute(vertex_gemm_kernel<VG_STRIDED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       VG_SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(vertex_gemm_kernel<VG_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, VG_SMEM_BYTES);
+  for (const void* f : {(const void*)vertex_gemm_kernel<VG_STRIDED, 128>, (const void*)vertex_gemm_kernel<VG_STRIDED, 64>,
+                        (const void*)vertex_gemm_kernel<VG_PACKED, 128>, (const void*)vertex_gemm_kernel<VG_PACKED, 64>}) {
+    cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, VG_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 cudaError_t launch_pack_vertex(const double* gre, const double* gim, int nf, int np, double* gp, cudaStream_t s) {
   const long long nrows = (long long)np * np, rp = vertex_rows_padded(np);
@@ -417,12 +422,19 @@ cudaError_t launch_pack_vertex(const double* gre, const double* gim, int nf, int
   return cudaGetLastError();
 }
 cudaError_t launch_vertex_gemm(const VgParams& p, cudaStream_t s) {
+  // the 64-wide N tile when the 128-wide tiling would compute > 10 % more padded columns
+  const long long n = p.mode == VG_PACKED ? (long long)p.nr * 16 : p.N;
+  const long long w128 = (n + 127) / 128 * 128, w64 = (n + 63) / 64 * 64;
+  const bool narrow = w64 * 10 < w128 * 9;
+  const unsigned ny = (unsigned)((narrow ? w64 : w128) / (narrow ? 64 : 128));
   if (p.mode == VG_PACKED) {
-    dim3 grid((unsigned)(p.nr * p.nk4), (unsigned)((p.nr * 16 + VG_BN - 1) / VG_BN), 1);
-    vertex_gemm_kernel<VG_PACKED><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
+    dim3 grid((unsigned)(p.nr * p.nk4), ny, 1);
+    if (narrow) vertex_gemm_kernel<VG_PACKED, 64><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
+    else vertex_gemm_kernel<VG_PACKED, 128><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
   } else {
-    dim3 grid((unsigned)((p.M + VG_BM - 1) / VG_BM), (unsigned)((p.N + VG_BN - 1) / VG_BN), (unsigned)(p.nb0 * p.nb1));
-    vertex_gemm_kernel<VG_STRIDED><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
+    dim3 grid((unsigned)((p.M + VG_BM - 1) / VG_BM), ny, (unsigned)(p.nb0 * p.nb1));
+    if (narrow) vertex_gemm_kernel<VG_STRIDED, 64><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
+    else vertex_gemm_kernel<VG_STRIDED, 128><<<grid, VG_THREADS, VG_SMEM_BYTES, s>>>(p);
   }
   return cudaGetLastError();
 }

@@ -410,7 +410,7 @@ int tn_contract(tn_handle_t h, double alpha, int a, const char* ia, int b, const
   const long long M = rpl - 256, N = rpr - 256;
   if (M > 2147483647LL || N > 2147483647LL || M * N >= (1LL << 32))
     return tn_fail(TN_ERR_UNSUPPORTED, "tn_contract: result of %lld x %lld elements (the index arithmetic is 32-bit)", M, N);
-  if ((N + 127) / 128 > 65535) return tn_fail(TN_ERR_UNSUPPORTED, "tn_contract: free dimension of the right operand too large (%lld)", N);
+  if ((N + 63) / 64 > 65535) return tn_fail(TN_ERR_UNSUPPORTED, "tn_contract: free dimension of the right operand too large (%lld)", N);
   VgParams p{};
   p.mode = VG_STRIDED;
   p.gp = h->wa; p.rows_padded = rpl;
