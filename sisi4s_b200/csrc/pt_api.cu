@@ -1048,8 +1048,13 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
         if (touched[z] && h->slot_of[z] < 0) missing.push_back(z);
       wave_of.assign(o, -1);
       const int m = (int)missing.size();
+      // waves pay (a few small launches) only when the copies are a visible share of the run: ~40 GB/s of
+      // host->device bandwidth against ~30 TFLOP/s of kernel; otherwise one wave = plain need-only upload
+      const double copy_s = (double)m * h->d.v * h->d.v * h->d.vd * 8.0 / 4.0e10;
+      const double kernel_s = 2.0 * h->d.v * h->d.v * (double)h->d.v * (h->d.vd + h->d.ol) * (double)weight / 3.0e13;
+      const bool split = copy_s > 0.02 * kernel_s;
       for (int c : {(m + 7) / 8, (m + 3) / 4, (m + 1) / 2, m})
-        if (c > 0 && (wave_end.empty() || c > wave_end.back())) wave_end.push_back(c);
+        if (c > 0 && (split || c == m) && (wave_end.empty() || c > wave_end.back())) wave_end.push_back(c);
       for (int q = 0, w = 0; q < m; ++q) {
         while (q >= wave_end[w]) ++w;
         wave_of[missing[q]] = w;
