@@ -236,29 +236,28 @@ class CcsdEnergyFromCoulombIntegralsReference(Algorithm):
                 V[b] = self.getTensorArgument(key)
             else:
                 missing.append(key)
+        vertex = None
         if missing:
+            # blocks the plan does not pass are built on the device from the vertex, when that is given
             if not self.isArgumentGiven("CoulombVertex"):
                 raise SisiException(f"Missing argument: {missing[0]}")
-            sub = {"CoulombVertex": self.arguments["CoulombVertex"], "HoleEigenEnergies": self.arguments["HoleEigenEnergies"],
-                   "ParticleEigenEnergies": self.arguments["ParticleEigenEnergies"]}
-            tmp = dict(self.data)
-            sub.update({k: "$" + k for k in missing})
-            CoulombIntegralsFromVertex(sub, tmp).run()
-            for k in missing:
-                V[k[:4]] = tmp[k]
-        out = []
+            vertex = self.getTensorArgument("CoulombVertex")
         mixer = _text(self, "mixer", "LinearMixer")
-        if mixer not in ("LinearMixer", "DiisMixer"):
+        if mixer not in ccsd.MIXERS:
             raise SisiException(f"Mixer not implemented: {mixer}")        # ClusterSinglesDoublesAlgorithm.cxx:50-54
-        res = ccsd.solve_ccsd(epsi, epsa, V, device=self.getIntegerArgument("device", 0), mixer=mixer,
-                              max_residua=self.getIntegerArgument("maxResidua", 4),
-                              mixing_ratio=self.getRealArgument("mixingRatio", 1.0),
-                              max_iterations=self.getIntegerArgument("maxIterations", ccsd.DEFAULT_MAX_ITERATIONS),
-                              energy_convergence=self.getRealArgument("energyConvergence", ccsd.DEFAULT_ENERGY_CONVERGENCE),
-                              amplitudes_convergence=self.getRealArgument("amplitudesConvergence", ccsd.DEFAULT_AMPLITUDES_CONVERGENCE),
-                              level_shift=self.getRealArgument("levelShift", ccsd.DEFAULT_LEVEL_SHIFT), log=out.append)
-        self.log = {"e": res["energy"]}
-        self.iterations = out
+        with ccsd.CcsdSolver(epsi, epsa, V, device=self.getIntegerArgument("device", 0), vertex=vertex) as solver:
+            if self.isArgumentGiven("initialSinglesAmplitudes") or self.isArgumentGiven("initialDoublesAmplitudes"):
+                solver.set_amplitudes(
+                    self.getTensorArgument("initialSinglesAmplitudes") if self.isArgumentGiven("initialSinglesAmplitudes") else None,
+                    self.getTensorArgument("initialDoublesAmplitudes") if self.isArgumentGiven("initialDoublesAmplitudes") else None)
+            res = solver.solve(mixer=mixer, max_residua=self.getIntegerArgument("maxResidua", 4),
+                               mixing_ratio=self.getRealArgument("mixingRatio", 1.0),
+                               max_iterations=self.getIntegerArgument("maxIterations", ccsd.DEFAULT_MAX_ITERATIONS),
+                               energy_convergence=self.getRealArgument("energyConvergence", ccsd.DEFAULT_ENERGY_CONVERGENCE),
+                               amplitudes_convergence=self.getRealArgument("amplitudesConvergence", ccsd.DEFAULT_AMPLITUDES_CONVERGENCE),
+                               level_shift=self.getRealArgument("levelShift", ccsd.DEFAULT_LEVEL_SHIFT))
+        self.log = {"e": res["energy"], "dir": res["direct"], "exc": res["exchange"]}
+        self.iterations = res["iterations"]
         self.converged = res["converged"]
         if not res["converged"]:
             self.note = "WARNING: energy or amplitudes convergence not reached."

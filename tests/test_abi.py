@@ -41,6 +41,17 @@ def test_tensor_engine_header_symbols_all_exported():
     for name in declared:
         assert hasattr(lib, name), name
     assert _lib.load().pt_estimate_device_bytes(40, 300, 0, 0) > 12e9      # host-only, no GPU needed
+    # include/sisi4s_ccsd.h (device CCSD solver)
+    from sisi4s_b200 import ccsd as CC
+    with open(os.path.join(ROOT, "include", "sisi4s_ccsd.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b(ccsd_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(CC.CCSD_SYMBOLS), declared ^ set(CC.CCSD_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    opt = CC.CcsdOptions()
+    CC._load().ccsd_default_options(C.byref(opt))
+    assert (opt.mixer, opt.max_iterations, opt.energy_convergence, opt.amplitudes_convergence) == (0, 16, 1e-6, 1e-5)
 
 
 def test_host_only_entry_points():
@@ -116,8 +127,9 @@ def test_plugin_class_compiles_against_reference_headers():
         pytest.skip("reference sources / g++ not present")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cuda_inc = "/usr/local/cuda/include"
-    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(root, "tests", "stubs"), "-I", ref,
-           "-I", os.path.join(root, "include"), "-I", cuda_inc, "-I", os.path.join(root, "sisi4s_b200", "csrc"),
-           os.path.join(root, "sisi4s_b200", "csrc", "CcsdPerturbativeTriplesGpu.cxx")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr[-3000:]
+    for src in ("CcsdPerturbativeTriplesGpu.cxx", "CcsdEnergyFromCoulombIntegralsGpu.cxx"):
+        cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(root, "tests", "stubs"), "-I", ref,
+               "-I", os.path.join(root, "include"), "-I", cuda_inc, "-I", os.path.join(root, "sisi4s_b200", "csrc"),
+               os.path.join(root, "sisi4s_b200", "csrc", src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        assert res.returncode == 0, (src, res.stderr[-3000:])

@@ -96,15 +96,35 @@ def test_residuum_matches_the_literal_oracle():
     Tabij = np.asfortranarray(0.1 * rng.standard_normal((v, v, o, o)))
     want_ai, want_abij = R.residuum(1, Tai, Tabij, V)
     with CcsdSolver(epsi, epsa, V) as s:
-        t1, t2 = s.eng.tensor((v, o), Tai), s.eng.tensor((v, v, o, o), Tabij)
-        r1, r2 = s.eng.tensor((v, o)), s.eng.tensor((v, v, o, o))
-        s.residuum(1, t1, t2, r1, r2)
-        assert np.abs(r1.get() - want_ai).max() <= 1e-12
-        assert np.abs(r2.get() - want_abij).max() <= 1e-12
-        e, _, _ = s.energy(t1, t2)
-        assert abs(e - R.energy(Tai, Tabij, V["PPHH"])) <= 1e-12
-        s.residuum(0, t1, t2, r1, r2)
-        assert np.abs(r2.get() - V["PPHH"]).max() == 0.0 and np.abs(r1.get()).max() == 0.0
+        r1, r2 = s.residuum(0)                            # no amplitudes given: the MP2 branch (:52-57)
+        assert np.abs(r2 - V["PPHH"]).max() == 0.0 and np.abs(r1).max() == 0.0
+        s.set_amplitudes(Tai, Tabij)
+        r1, r2 = s.residuum(1)
+        assert np.abs(r1 - want_ai).max() <= 1e-12
+        assert np.abs(r2 - want_abij).max() <= 1e-12
+        res = s.solve(max_iterations=0)                   # "computing energy from given amplitudes" (:116-119)
+        assert abs(res["energy"] - R.energy(Tai, Tabij, V["PPHH"])) <= 1e-12
+        assert np.array_equal(res["T2"], Tabij)
+
+
+def test_integrals_from_the_vertex_inside_the_solver():
+    """ccsd_set_vertex: the six blocks getResiduum reads, built on the device with the index strings of
+    CoulombIntegralsFromVertex.cxx:395-431, equal the NumPy restatement; solving from the vertex alone gives
+    the same energy as solving from the blocks."""
+    from oracle import ccsd_ref as R
+    from sisi4s_b200.ccsd import CcsdSolver, BLOCKS
+    o, v = 3, 6
+    epsi, epsa = S.eigenenergies(o, v)
+    gamma = S.make_vertex(o, v, seed=4, nf=14, kappa=0.4)
+    V = R.integral_blocks(gamma, o, v)
+    kw = dict(mixer="DiisMixer", max_iterations=40, energy_convergence=1e-11, amplitudes_convergence=1e-10)
+    with CcsdSolver(epsi, epsa, vertex=gamma) as s:
+        for b in BLOCKS:
+            assert np.abs(s.get_integrals(b) - V[b]).max() <= 1e-13, b
+        a = s.solve(**kw)
+    with CcsdSolver(epsi, epsa, V) as s:
+        b = s.solve(**kw)
+    assert a["converged"] and abs(a["energy"] - b["energy"]) <= 1e-12
 
 
 @pytest.mark.parametrize("mixer", ["DiisMixer", "LinearMixer"])
