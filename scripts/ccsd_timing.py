@@ -16,6 +16,8 @@ t0 = time.time()
 with CcsdSolver(epsi, epsa, vertex=gamma) as s:       # the six integral blocks are built on the device
     V = {b: s.get_integrals(b) for b in ("PPHH", "PHPH", "HHHH", "HHHP", "PPPH", "PPPP")} if v <= 40 else None
     out["integrals_s"] = time.time() - t0
+    s.solve(mixer="DiisMixer", max_iterations=2)          # warm-up: workspace allocation, first launches
+    s.set_amplitudes(np.zeros((v, o)), np.zeros((v, v, o, o)))
     t0 = time.time()
     res = s.solve(mixer="DiisMixer", max_iterations=iters, energy_convergence=1e-14, amplitudes_convergence=1e-14)
     dt = time.time() - t0
