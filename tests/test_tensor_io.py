@@ -181,3 +181,34 @@ def test_ftoddump_reader_follows_the_reference_layout(tmp_path):
     open(p, "wb").write(b"notafile" + raw[8:])
     with pytest.raises(TIO.TensorFormatError, match="Invalid file format"):
         TIO.read_ftoddump(p)
+
+
+def test_file_headers_match_the_structs_of_the_reference_headers(tmp_path):
+    """oracle/_ref/file_formats.txt is printed by a program compiled against the reference's OWN
+    src/util/BinaryTensorFormat.hpp and src/algorithms/CoulombVertexReader.hpp (oracle/ref_format_dump.cxx):
+    the bytes of a TENS header / dimension headers and the layout of the FTODDUMP structs.  The writers here
+    must produce exactly those bytes."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "file_formats.txt")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not built (reference tree absent)")
+    ref = {}
+    for line in open(path):
+        tag, *rest = line.split()
+        ref[tag] = rest
+    hexbytes = lambda tag: bytes(int(x, 16) for x in ref[tag])
+    p = str(tmp_path / "t.bin")
+    TIO.write_binary(p, np.zeros((5, 7, 3, 2), order="F"))
+    raw = open(p, "rb").read()
+    assert raw[:32] == hexbytes("tens_real_order4")
+    for dim in range(4):
+        assert raw[32 + 8 * dim:40 + 8 * dim] == hexbytes(f"tens_dim{dim}")
+    assert len(raw) == 32 + 4 * 8 + 8 * 5 * 7 * 3 * 2
+    TIO.write_binary(p, np.zeros((2, 3, 4), dtype=complex, order="F"))
+    assert open(p, "rb").read()[:32] == hexbytes("tens_complex_order3")
+    # the first line reads "sizeof_header 32 sizeof_dim 8"
+    assert ref["sizeof_header"][0] == "32" and ref["sizeof_header"][2] == "8"
+    # FTODDUMP structs: Header = magic[8] + 6 int32, Chunk = magic[8] + int64 size
+    f = dict(zip(ref["ftod_header"][0::2], (int(x) for x in ref["ftod_header"][1::2])))
+    assert f == {"size": TIO._FTOD_HEADER.size, "magic": 0, "No": 8, "Nv": 12, "NG": 16, "NSpins": 20, "kPoints": 24, "reserved": 28}
+    c = dict(zip(ref["ftod_chunk"][0::2], (int(x) for x in ref["ftod_chunk"][1::2])))
+    assert c == {"size": TIO._FTOD_CHUNK.size, "magic": 0, "size_field": 8, "magic_len": 8}
