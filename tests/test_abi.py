@@ -54,6 +54,18 @@ def test_tensor_engine_header_symbols_all_exported():
     assert (opt.mixer, opt.max_iterations, opt.energy_convergence, opt.amplitudes_convergence) == (0, 16, 1e-6, 1e-5)
 
 
+def test_headers_are_plain_c():
+    """The drop-in boundary is a C ABI: the three headers compile as C99 (no C++ types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not present")
+    src = '#include "sisi4s_pt.h"\n#include "sisi4s_tn.h"\n#include "sisi4s_ccsd.h"\nint main(void){PtStats s; CcsdOptions o; (void)s; (void)o; return 0;}\n'
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                         input=src, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+
+
 def test_host_only_entry_points():
     _ensure_built()
     lib = _lib.load()
