@@ -191,6 +191,12 @@ int64_t pt_num_triples(int o);
 /* contiguous share [begin,end) of the sorted-triple enumeration for `rank` of
  * `nranks`, balanced by the number of distinct hole permutations (6/3/3/1)    */
 int pt_partition(int o, int nranks, int rank, int64_t *begin, int64_t *end);
+/* Host-only preview of the hole-block walk pt_run does with option "hole_block" = b over the sorted
+ * triples [begin,end): number of groups (= launches), the largest number of active holes of a group
+ * (<= 3b: what the device buffers are sized for) and the number of PPPH slab (re)builds with 3b slots.
+ * No GPU needed; used to size a run (at o=100, b=6: 969 groups for the whole problem).          */
+int pt_plan_hole_blocks(int o, int hole_block, int64_t begin, int64_t end, int64_t *n_groups,
+                        int32_t *max_active_holes, int64_t *slab_loads);
 /* Computes sum_{t in [begin,end)} E_t, the (T) energy contribution of those
  * sorted triples (the body of the reference loop, :159-216).  e_triples: the
  * sum; e_per_triple: NULL or end-begin doubles.  The caller adds CcsdEnergy

@@ -61,6 +61,8 @@ SYMBOLS = {
     "pt_set_vertex": (C.c_int, [_H, C.c_int, C.c_int, _DP, _DP]),
     "pt_num_triples": (C.c_int64, [C.c_int]),
     "pt_partition": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "pt_plan_hole_blocks": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int64)]),
     "pt_run": (C.c_int, [_H, C.c_int64, C.c_int64, _DP, _DP]),
     "pt_run_list": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_int64), _DP, _DP]),
     "pt_get_stats": (C.c_int, [_H, C.POINTER(PtStats)]),

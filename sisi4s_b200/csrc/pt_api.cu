@@ -163,6 +163,22 @@ inline int triple_weight(const Triple& t) {
   return w[triple_class(t)];
 }
 
+// hole-block walk: a sorted triple belongs to the group of the hole blocks (I<=J<=K) of width bw it touches;
+// K runs fastest in the key, so consecutive groups share the blocks I and J
+inline long long block_key(int i, int j, int k, int bw, long long nb) {
+  return ((long long)(i / bw) * nb + j / bw) * nb + k / bw;
+}
+// ... and needs the holes of those (at most three distinct) blocks, ascending
+std::vector<int> group_holes(int i, int j, int k, int bw, int o) {
+  std::vector<int> holes;
+  const int first[3] = {i / bw * bw, j / bw * bw, k / bw * bw};
+  for (int m = 0; m < 3; ++m)
+    for (int z = first[m]; z < std::min(first[m] + bw, o); ++z)
+      if (std::find(holes.begin(), holes.end(), z) == holes.end()) holes.push_back(z);
+  std::sort(holes.begin(), holes.end());
+  return holes;
+}
+
 // device time of the uploads + packing: one event window per synchronous setter, one window over
 // all of them in async mode (closed by pt_sync / pt_run)
 struct UploadScope {
@@ -376,6 +392,56 @@ int64_t pt_estimate_device_bytes(int o, int v, int slab_slots, int hole_block) {
   if (hole_block > 0) n += vv * std::max((double)oa * oa, (double)o) + (double)o * o * o * v;   /* T2 staging, full HHHP */
   const double nr = d.nr;
   return (int64_t)(8.0 * n + 4.0 * nr * (nr + 1) * (nr + 2) / 6);
+}
+
+int pt_plan_hole_blocks(int o, int hole_block, int64_t begin, int64_t end, int64_t* n_groups, int32_t* max_active_holes,
+                        int64_t* slab_loads) {
+  if (o < 1 || hole_block < 1 || begin < 0 || begin > end || end > pt_num_triples(o))
+    return fail(PT_ERR_INVALID, "pt_plan_hole_blocks: bad arguments");
+  std::vector<Triple> tr;
+  enumerate_triples(o, tr);
+  const int bw = std::min(hole_block, o);
+  const long long nb = (o + bw - 1) / bw;
+  const int slots = std::min(3 * bw, o);
+  std::vector<std::pair<long long, Triple>> keyed;
+  for (int64_t n = begin; n < end; ++n)
+    if (triple_class(tr[n]) != 3) keyed.push_back({block_key(tr[n].i, tr[n].j, tr[n].k, bw, nb), tr[n]});
+  std::stable_sort(keyed.begin(), keyed.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  // the walk pt_run does: one group per key; slabs kept in `slots` slots with LRU replacement
+  int64_t groups = 0, loads = 0;
+  int32_t max_active = 0;
+  std::vector<long long> tick(o, -1);   // last use of a resident slab, -1 = not resident
+  int resident = 0;
+  long long now = 0;
+  for (size_t g0 = 0; g0 < keyed.size();) {
+    size_t g1 = g0;
+    while (g1 < keyed.size() && keyed[g1].first == keyed[g0].first) ++g1;
+    const std::vector<int> holes = group_holes(keyed[g0].second.i, keyed[g0].second.j, keyed[g0].second.k, bw, o);
+    max_active = std::max<int32_t>(max_active, (int32_t)holes.size());
+    ++now;
+    for (int z : holes)
+      if (tick[z] >= 0) tick[z] = now;
+    for (int z : holes) {
+      if (tick[z] >= 0) continue;
+      if (resident == slots) {   // evict the least recently used slab that this group does not need
+        int victim = -1;
+        for (int q = 0; q < o; ++q)
+          if (tick[q] >= 0 && tick[q] != now && (victim < 0 || tick[q] < tick[victim])) victim = q;
+        if (victim < 0) return fail(PT_ERR_INVALID, "pt_plan_hole_blocks: %zu slabs needed, %d slots", holes.size(), slots);
+        tick[victim] = -1;
+        --resident;
+      }
+      tick[z] = now;
+      ++resident;
+      ++loads;
+    }
+    ++groups;
+    g0 = g1;
+  }
+  if (n_groups) *n_groups = groups;
+  if (max_active_holes) *max_active_holes = max_active;
+  if (slab_loads) *slab_loads = loads;
+  return PT_OK;
 }
 
 int pt_create(pt_handle_t* out, int o, int v, int device) { return pt_create_ex(out, o, o, v, device); }
@@ -1063,7 +1129,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
     for (size_t n = 0; n < tr.size(); ++n) {
       const int c = triple_class(tr[n]);
       if (c == 3) continue;
-      long long key = grouped ? ((long long)(tr[n].i / bw) * nb + tr[n].j / bw) * nb + tr[n].k / bw : 0;
+      long long key = grouped ? block_key(tr[n].i, tr[n].j, tr[n].k, bw, nb) : 0;
       if (!missing.empty()) key = std::max(0, std::max(wave_of[tr[n].i], std::max(wave_of[tr[n].j], wave_of[tr[n].k])));
       ent.push_back({make_int4(tr[n].i, tr[n].j, tr[n].k, c), (int)n, key});
     }
@@ -1097,11 +1163,7 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
         while (g1 < ent.size() && ent[g1].key == ent[g0].key) ++g1;
         Group g{g0, g1, {}};
         if (grouped) {
-          const int first[3] = {ent[g0].t.x / bw * bw, ent[g0].t.y / bw * bw, ent[g0].t.z / bw * bw};
-          for (int m = 0; m < 3; ++m)
-            for (int z = first[m]; z < std::min(first[m] + bw, o); ++z)
-              if (std::find(g.holes.begin(), g.holes.end(), z) == g.holes.end()) g.holes.push_back(z);
-          std::sort(g.holes.begin(), g.holes.end());
+          g.holes = group_holes(ent[g0].t.x, ent[g0].t.y, ent[g0].t.z, bw, o);
         }
         for (size_t n = g0; n < g1; ++n) {
           int4 t = ent[n].t;

@@ -145,3 +145,35 @@ def test_plugin_class_compiles_against_reference_headers():
                os.path.join(root, "sisi4s_b200", "csrc", src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         assert res.returncode == 0, (src, res.stderr[-3000:])
+
+
+def test_hole_block_walk_plan_on_the_host():
+    """pt_plan_hole_blocks: the grouping pt_run uses in hole_block mode (same key / hole functions), without a
+    GPU: groups tile a rank's range, at most 3b active holes, slab loads bounded by groups * 3b; the
+    config-5 shape (o=100, b=6) has 969 hole-block triples."""
+    _ensure_built()
+    lib = _lib.load()
+
+    def plan(o, b, begin, end):
+        g, a, s = C.c_int64(), C.c_int32(), C.c_int64()
+        assert lib.pt_plan_hole_blocks(o, b, begin, end, C.byref(g), C.byref(a), C.byref(s)) == 0
+        return g.value, a.value, s.value
+
+    g, a, s = plan(100, 6, 0, lib.pt_num_triples(100))
+    assert g == 17 * 18 * 19 // 6 == 969 and a == 18
+    assert 100 <= s <= g * 18 and s < 0.4 * g * 18          # consecutive groups share the slabs of blocks I and J
+    for o, b in ((7, 2), (7, 3), (10, 4), (5, 8), (40, 8)):
+        total = lib.pt_num_triples(o)
+        nb = -(-o // min(b, o))
+        g, a, s = plan(o, b, 0, total)
+        full = nb * (nb + 1) * (nb + 2) // 6          # a one-hole last block has no triple besides the skipped i=j=k
+        assert full - 1 <= g <= full and a <= min(3 * b, o) and s >= o
+        # ranks' contiguous ranges: every group of the whole problem is visited by at least one rank,
+        # and the per-rank walks together do not need many more launches than the whole problem
+        parts = 0
+        for r in range(4):
+            lo, hi = C.c_int64(), C.c_int64()
+            lib.pt_partition(o, 4, r, C.byref(lo), C.byref(hi))
+            parts += plan(o, b, lo.value, hi.value)[0]
+        assert g <= parts <= g + 3 * nb * nb
+    assert lib.pt_plan_hole_blocks(5, 0, 0, 1, None, None, None) == -1
