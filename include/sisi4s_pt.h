@@ -207,6 +207,19 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double *e_triples, double 
 int pt_run_list(pt_handle_t h, int64_t n, const int64_t *triples, double *e_triples, double *e_per_triple);
 int pt_get_stats(pt_handle_t h, PtStats *stats);
 
+/* ---- complex closed-shell step -------------------------------- */
+/* Re E(T) of CcsdPerturbativeTriplesComplex::Calculator<complex>::calculate (reference
+ * src/algorithms/CcsdPerturbativeTriplesComplex.cxx:166-271, particle term :341-348, hole term from
+ * PHHHCoulombIntegrals["clkj"] :135-140, conj(DV / Delta) :224-230).  Every complex tensor is given as its
+ * real and imaginary part (column-major, the reference's index order): T1[v,o], T2[v,v,o,o],
+ * PPHH[v,v,o,o], PHHH[v,o,o,o], CoulombVertex[NF,Np,Np].  One call = two passes of the real step's fused
+ * kernel with Re/Im stacked along the contracted indices (4x the real step's work).  e_per_triple: NULL or
+ * o(o+1)(o+2)/6 doubles.                                                                         */
+int pt_complex_triples(int o, int v, int device, const double *epsi, const double *epsa, const double *t1_re,
+                       const double *t1_im, const double *t2_re, const double *t2_im, const double *pphh_re,
+                       const double *pphh_im, const double *phhh_re, const double *phhh_im, int nf, int np,
+                       const double *gamma_re, const double *gamma_im, double *e_triples, double *e_per_triple);
+
 /* ---- debug / measurement helpers (not part of the drop-in contract) ------- */
 /* one 16x16x16 tile of W_{xyz}[a,b,c] (getDoublesContribution) computed by the
  * fused kernel's own main loop; out[la + 16*(lb + 16*lc)]                     */

@@ -22,63 +22,45 @@ imaginary parts stacked along the contracted index:
 
 so the big stacked integrals [V_r ; V_i] are packed once and shared by both passes.  Cost: 4x the real
 step, as complex arithmetic demands.  The complex PPPH block V[b,c,d,k] = sum_F conj(G[F,d,b]) G[F,c,k]
-is built on the device by the tensor engine.
+is built on the device by the tensor engine.  The driver itself lives in the library
+(`pt_complex_triples`, csrc/pt_complex.cu); this module binds it and registers the plan step.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 
-from .tensor_engine import DeviceTensors
-from .triples import Algorithm, SisiException, TriplesEngine, register
-
-
-def complex_ppph_from_vertex(gamma, o, v, device=0):
-    """(V_r, V_i)[b,c,d,k] of V = conj(GammaFab)["Fdb"] GammaFai["Fck"] (:341-348), column-major [v,v,v,o]."""
-    np_ = gamma.shape[1]
-    a0 = np_ - v
-    gab, gai = gamma[:, a0:, a0:], gamma[:, a0:, :o]
-    with DeviceTensors(device) as eng:
-        abr, abi = eng.tensor(gab.shape, gab.real), eng.tensor(gab.shape, gab.imag)
-        air, aii = eng.tensor(gai.shape, gai.real), eng.tensor(gai.shape, gai.imag)
-        vr, vi = eng.tensor((v, v, v, o)), eng.tensor((v, v, v, o))
-        eng.contract(1.0, abr, "Fdb", air, "Fck", 0.0, vr, "bcdk")      # Re: ab_r ai_r + ab_i ai_i
-        eng.contract(1.0, abi, "Fdb", aii, "Fck", 1.0, vr, "bcdk")
-        eng.contract(1.0, abr, "Fdb", aii, "Fck", 0.0, vi, "bcdk")      # Im: ab_r ai_i - ab_i ai_r
-        eng.contract(-1.0, abi, "Fdb", air, "Fck", 1.0, vi, "bcdk")
-        return vr.get(), vi.get()
+from . import _lib
+from .triples import Algorithm, SisiException, register
 
 
 def complex_triples_energy(epsi, epsa, T1, T2, Vpphh, Vphhh, gamma, device: int = 0, return_per_triple=False):
-    """Re E(T) of the complex closed-shell step.  T1[v,o], T2[v,v,o,o], Vpphh[v,v,o,o], Vphhh[v,o,o,o],
-    gamma[NF,Np,Np] (complex or real arrays, column-major index order of the reference)."""
+    """Re E(T) of the complex closed-shell step through the C ABI (pt_complex_triples, csrc/pt_complex.cu).
+    T1[v,o], T2[v,v,o,o], Vpphh[v,v,o,o], Vphhh[v,o,o,o], gamma[NF,Np,Np] (complex or real arrays,
+    column-major index order of the reference)."""
+    lib = _lib.load()
     o, v = int(len(epsi)), int(len(epsa))
-    c = lambda a: np.asarray(a, dtype=np.complex128)
-    T1, T2, P, U = c(T1), c(T2), c(Vpphh), np.einsum("clzy->yzlc", c(Vphhh))     # U[y,z,l,c] = Vphhh[c,l,z,y]
-    vr, vi = complex_ppph_from_vertex(np.asarray(gamma), o, v, device)
-    f = np.asfortranarray
-    ppph_e = f(np.concatenate([vr, vi], axis=2))                  # [v,v,2v,o]: [V_r ; V_i] along d
-    hhhp_e = f(np.concatenate([U.real, U.imag], axis=2))          # [o,o,2o,v]: [U_r ; U_i] along l
-    total, per = 0.0, None
-    with TriplesEngine(o, v, device=device, o_all=2 * o, vd=2 * v) as eng:
-        eng.set_eigenenergies(epsi, epsa)
-        eng.set_hhhp(hhhp_e)
-        eng.set_ppph(ppph_e)
-        for part in ("re", "im"):
-            if part == "re":    # W_r, S_r
-                ta, tb = T2.real, -T2.imag
-                s1, s2 = (T1.real, P.real), (-T1.imag, P.imag)
-            else:               # W_i, S_i
-                ta, tb = T2.imag, T2.real
-                s1, s2 = (T1.real, P.imag), (T1.imag, P.real)
-            eng.set_doubles(f(np.concatenate([ta, tb], axis=1)))          # [v,2v,o,o]
-            eng.set_doubles_hole(f(np.concatenate([ta, tb], axis=3)))     # [v,v,o,2o]
-            eng.set_singles(f(s1[0])); eng.set_pphh(f(s1[1]))
-            eng.set_singles_pair(f(s2[0]), f(s2[1]))
-            res = eng.run()
-            total += res.energy
-            per = res.per_triple if per is None else per + res.per_triple
-        stats = eng.stats()
-    return (total, per, stats) if return_per_triple else total
+    f = lambda a: np.asfortranarray(a, dtype=np.float64)
+    parts = []
+    for a, shape, name in ((T1, (v, o), "CcsdSinglesAmplitudes"), (T2, (v, v, o, o), "CcsdDoublesAmplitudes"),
+                           (Vpphh, (v, v, o, o), "PPHHCoulombIntegrals"), (Vphhh, (v, o, o, o), "PHHHCoulombIntegrals")):
+        a = np.asarray(a)
+        if tuple(a.shape) != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+        parts += [f(a.real), f(a.imag) if np.iscomplexobj(a) else np.zeros(shape, order="F")]
+    g = np.asarray(gamma)
+    nf, np_, np2 = g.shape
+    if np_ != np2 or np_ < o + v:
+        raise ValueError("CoulombVertex must be [NF,Np,Np] with Np >= No + Nv")
+    gre, gim = f(g.real), (f(g.imag) if np.iscomplexobj(g) else np.zeros(g.shape, order="F"))
+    ei, ea = f(epsi), f(epsa)
+    per = np.zeros(o * (o + 1) * (o + 2) // 6)
+    e = C.c_double(0.0)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _lib.check(lib.pt_complex_triples(o, v, int(device), p(ei), p(ea), *[p(a) for a in parts], nf, np_, p(gre), p(gim),
+                                      C.byref(e), p(per)))
+    return (float(e.value), per) if return_per_triple else float(e.value)
 
 
 @register

@@ -35,11 +35,10 @@ def test_complex_triples_match_the_oracle(o, v, nf, seed):
     from sisi4s_b200.triples_complex import complex_triples_energy
     epsi, epsa, T1, T2, P, U, g = _complex_inputs(o, v, nf, seed)
     e_ref, per_ref = OC.triples_complex(epsi, epsa, T1, T2, P, U, g, return_per_triple=True)
-    e, per, st = complex_triples_energy(epsi, epsa, T1, T2, P, U, g, return_per_triple=True)
+    e, per = complex_triples_energy(epsi, epsa, T1, T2, P, U, g, return_per_triple=True)
     scale = max(1.0, np.abs(per_ref).max())
     assert np.abs(per - per_ref.real).max() <= 1e-11 * scale, (per, per_ref.real)
     assert abs(e - e_ref.real) <= 1e-11 * max(1.0, abs(e_ref))
-    assert st.kernel_launches > 0
 
 
 @pytest.mark.gpu
@@ -52,7 +51,7 @@ def test_complex_path_with_real_inputs_is_the_real_step():
         eng.set_inputs(*inp.args())
         base = eng.run()
     greal = np.concatenate([inp.Gamma.real, inp.Gamma.imag], axis=0)
-    e, per, _ = complex_triples_energy(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh,
+    e, per = complex_triples_energy(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh,
                                        np.einsum("jklc->clkj", inp.Vhhhp), greal, return_per_triple=True)
     assert abs(e - base.energy) <= 1e-12
     assert np.abs(per - base.per_triple).max() <= 1e-12
