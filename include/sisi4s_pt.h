@@ -220,6 +220,15 @@ int pt_complex_triples(int o, int v, int device, const double *epsi, const doubl
                        const double *pphh_im, const double *phhh_re, const double *phhh_im, int nf, int np,
                        const double *gamma_re, const double *gamma_im, double *e_triples, double *e_per_triple);
 
+/* Spin-orbital (unrestricted) triples, UPerturbativeTriples::run (reference
+ * src/algorithms/UPerturbativeTriples.cxx:19-305): full-tensor form on ANTISYMMETRISED integrals
+ * PPHH[v,v,o,o], HHHP[o,o,o,v], PPPH[v,v,v,o] and spin-orbital amplitudes; returns the triples energy alone
+ * (the reference's PerturbativeTriplesEnergy, :305).  Three v^3 o^3 device tensors: small systems, as in the
+ * reference.                                                                                     */
+int pt_spin_orbital_triples(int o, int v, int device, const double *epsi, const double *epsa, const double *tai,
+                            const double *tabij, const double *vabij, const double *vijka, const double *vabci,
+                            double *e_triples);
+
 /* ---- debug / measurement helpers (not part of the drop-in contract) ------- */
 /* one 16x16x16 tile of W_{xyz}[a,b,c] (getDoublesContribution) computed by the
  * fused kernel's own main loop; out[la + 16*(lb + 16*lc)]                     */

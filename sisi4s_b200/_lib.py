@@ -66,6 +66,7 @@ SYMBOLS = {
     "pt_run": (C.c_int, [_H, C.c_int64, C.c_int64, _DP, _DP]),
     "pt_run_list": (C.c_int, [_H, C.c_int64, C.POINTER(C.c_int64), _DP, _DP]),
     "pt_get_stats": (C.c_int, [_H, C.POINTER(PtStats)]),
+    "pt_spin_orbital_triples": (C.c_int, [C.c_int, C.c_int, C.c_int] + [_DP] * 8),
     "pt_complex_triples": (C.c_int, [C.c_int, C.c_int, C.c_int] + [_DP] * 10 + [C.c_int, C.c_int, _DP, _DP, _DP, _DP]),
     "pt_debug_w_tile": (C.c_int, [_H] + [C.c_int] * 6 + [_DP]),
     "pt_bench_fp64": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, _DP, _DP]),

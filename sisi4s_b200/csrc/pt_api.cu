@@ -29,6 +29,15 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+// library-internal: lets the other translation units (upt.cu) report through pt_last_error()
+namespace pt {
+int record_error(int code, const char* message) { return fail(code, "%s", message); }
+}  // namespace pt
+
+namespace {
+
 #define CU(call)                                                                         \
   do {                                                                                   \
     cudaError_t e_ = (call);                                                             \

@@ -140,7 +140,7 @@ def test_plugin_class_compiles_against_reference_headers():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cuda_inc = "/usr/local/cuda/include"
     for src in ("CcsdPerturbativeTriplesGpu.cxx", "CcsdEnergyFromCoulombIntegralsGpu.cxx",
-                "CcsdPerturbativeTriplesComplexGpu.cxx"):
+                "CcsdPerturbativeTriplesComplexGpu.cxx", "UPerturbativeTriplesGpu.cxx"):
         cmd = ["g++", "-std=c++17", "-fsyntax-only", "-w", "-I", os.path.join(root, "tests", "stubs"), "-I", ref,
                "-I", os.path.join(root, "include"), "-I", cuda_inc, "-I", os.path.join(root, "sisi4s_b200", "csrc"),
                os.path.join(root, "sisi4s_b200", "csrc", src)]
