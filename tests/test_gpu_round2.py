@@ -24,6 +24,15 @@ def _triples(o):
 
 
 # ------------------------------------------------------------ parity at the metric's own shapes
+def _golden_o40v300():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "o40v300_triples.json")) as f:
+        g = json.load(f)
+    assert (g["o"], g["v"], g["seed"], g["nf"]) == (40, 300, 2026, 24)
+    return g
+
+
 def test_o40_v300_sampled_triples_match_c_oracle():
     """BASELINE configs[2] -- the shape the metric is quoted on -- CUDA path vs oracle/pt_oracle.c on
     sampled sorted triples covering all four hole classes (i<j<k, i=j<k, i<j=k, i=j=k)."""
@@ -37,6 +46,13 @@ def test_o40_v300_sampled_triples_match_c_oracle():
         eng.set_inputs(inp.epsi, inp.epsa, inp.T1, inp.T2, inp.Vpphh, inp.Vhhhp, inp.Vppph)
         got = eng.run_list(picks).per_triple
         again = eng.run_list(picks[::-1]).per_triple[::-1]
+        gold = _golden_o40v300()
+        got200 = eng.run_list(gold["index"]).per_triple
+    # 200 triples computed ahead of time by the same oracle on the same host-generated inputs
+    # (tests/golden/make_o40v300_triples.py; the box's oracle has time for the ten picked here)
+    want200 = np.array([float.fromhex(x) for x in gold["energy"]])
+    assert len(want200) >= 200 and np.abs(got200 - want200).max() <= ABS_TOL
+    assert abs(got200.sum() - want200.sum()) <= ABS_TOL
     CO.use_blas(True)
     ref = CO.triples_list(*inp.args(), np.array(picks))
     assert np.abs(got - ref).max() <= ABS_TOL, (got, ref)
