@@ -111,6 +111,41 @@ def test_no_cpu_fallback_without_gpu():
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
 
 
+def test_every_product_entry_point_fails_loudly_without_gpu():
+    """Complex and spin-orbital triples, the tensor engine and the CCSD solver: an error with a message, never
+    a number computed somewhere else."""
+    from conftest import gpu_available
+    if gpu_available():
+        pytest.skip("CUDA device present")
+    _ensure_built()
+    import numpy as np
+    from sisi4s_b200 import synthetic as S
+    from sisi4s_b200.ccsd import CcsdSolver
+    from sisi4s_b200.tensor_engine import DeviceTensors, TnError
+    from sisi4s_b200.triples_complex import complex_triples_energy
+    from sisi4s_b200.triples_spin_orbital import spin_orbital_triples_energy
+    o, v = 2, 3
+    ei, ea = S.eigenenergies(o, v)
+    z = lambda *shape: np.zeros(shape, order="F")
+    with pytest.raises(_lib.PtError):
+        spin_orbital_triples_energy(ei, ea, z(v, o), z(v, v, o, o), z(v, v, o, o), z(o, o, o, v), z(v, v, v, o))
+    assert lib_message()
+    with pytest.raises(_lib.PtError):
+        complex_triples_energy(ei, ea, z(v, o) + 0j, z(v, v, o, o) + 0j, z(v, v, o, o) + 0j, z(v, o, o, o) + 0j,
+                               np.zeros((4, o + v, o + v), dtype=complex))
+    with pytest.raises(TnError):
+        DeviceTensors(0)
+    with pytest.raises(TnError):
+        CcsdSolver(ei, ea, vertex=np.zeros((4, o + v, o + v), dtype=complex))
+    # bad arguments are rejected before any device work
+    with pytest.raises(ValueError):
+        spin_orbital_triples_energy(ei, ea, z(v, o), z(v, v, o, o), z(v, v, o, o), z(o, o, o, v), z(v, v, o, o))
+
+
+def lib_message():
+    return _lib.load().pt_last_error().decode()
+
+
 def test_plugin_mirror_argument_errors():
     # mirrors Algorithm::getTensorArgument / setRealArgument error behaviour
     # (reference src/algorithms/Algorithm.cxx:37-55, 364-367)
