@@ -38,7 +38,7 @@ typedef enum PtStatus {
   PT_ERR_INVALID = -1,   /* bad argument / call order                          */
   PT_ERR_CUDA = -2,      /* CUDA runtime error (message in pt_last_error)      */
   PT_ERR_MISSING = -3,   /* an input tensor was not set before pt_run          */
-  PT_ERR_NOMEM = -4,     /* device memory exhausted                            */
+  PT_ERR_NOMEM = -4,     /* device or host memory exhausted                    */
   PT_ERR_UNSUPPORTED = -5
 } PtStatus;
 

@@ -23,6 +23,11 @@
 #include "../../include/sisi4s_ccsd.h"
 #include "../../include/sisi4s_tn.h"
 
+namespace pt {
+int tn_record_error(int code, const char* message);   // tn_engine.cu: what tn_last_error() returns
+int tn_on_exception(const char* where);
+}  // namespace pt
+
 namespace {
 
 #define CRC(call)                     \
@@ -92,7 +97,7 @@ int ensure_block(ccsd_handle_t h, const std::string& name, int* id) {
   static const char* names[] = {"PPHH", "PHPH", "HHHH", "HHHP", "PPPH", "PPPP"};
   bool ok = false;
   for (const char* n : names) ok = ok || name == n;
-  if (!ok) return TN_ERR_INVALID;
+  if (!ok) return pt::tn_record_error(TN_ERR_INVALID, ("unknown integral block " + name + " (PPHH, PHPH, HHHH, HHHP, PPPH, PPPP)").c_str());
   auto it = h->V.find(name);
   if (it == h->V.end()) {
     Shape s = block_shape(h, name);
@@ -112,7 +117,7 @@ int build_x(ccsd_handle_t h, int Tai, int Tabij) {   // Xabij["abij"] = Tabij["a
 // getResiduum(i, amplitudes) into Rai, Rabij (:29-295)
 int residuum(ccsd_handle_t h, int iteration, int Tai, int Tabij, int Rai, int Rabij) {
   for (const char* n : {"PPHH", "PHPH", "HHHH", "HHHP", "PPPH", "PPPP"})
-    if (!h->V.count(n)) return TN_ERR_INVALID;
+    if (!h->V.count(n)) return pt::tn_record_error(TN_ERR_INVALID, (std::string("Missing argument: ") + n + "CoulombIntegrals").c_str());
   const int Vabij = h->V["PPHH"], Vaibj = h->V["PHPH"], Vijkl = h->V["HHHH"], Vijka = h->V["HHHP"], Vabci = h->V["PPPH"],
             Vabcd = h->V["PPPP"];
   if (iteration == 0 && !h->initial_doubles) {
@@ -240,8 +245,8 @@ void ccsd_default_options(CcsdOptions* opt) {
   opt->level_shift = 0.0;
 }
 
-int ccsd_create(ccsd_handle_t* out, int o, int v, int device) {
-  if (!out || o < 1 || v < 1) return TN_ERR_INVALID;
+int ccsd_create(ccsd_handle_t* out, int o, int v, int device) try {
+  if (!out || o < 1 || v < 1) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_create: bad arguments");
   ccsd_handle_t h = new CcsdHandle_();
   h->o = o; h->v = v;
   int rc = tn_create(&h->tn, device);
@@ -256,37 +261,47 @@ int ccsd_create(ccsd_handle_t* out, int o, int v, int device) {
   if (rc) { ccsd_destroy(h); return rc; }
   *out = h;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_create");
 }
 
-int ccsd_destroy(ccsd_handle_t h) {
+int ccsd_destroy(ccsd_handle_t h) try {
   if (!h) return TN_OK;
   if (h->tn) tn_destroy(h->tn);   // frees every tensor of the engine
   delete h;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_destroy");
 }
 
-int ccsd_set_eigenenergies(ccsd_handle_t h, const double* epsi, const double* epsa) {
-  if (!h || !epsi || !epsa) return TN_ERR_INVALID;
+int ccsd_set_eigenenergies(ccsd_handle_t h, const double* epsi, const double* epsa) try {
+  if (!h || !epsi || !epsa) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_set_eigenenergies: bad arguments");
   CRC(tn_upload(h->tn, h->epsi, epsi));
   return tn_upload(h->tn, h->epsa, epsa);
+} catch (...) {
+  return pt::tn_on_exception("ccsd_set_eigenenergies");
 }
 
-int ccsd_set_integrals(ccsd_handle_t h, const char* name, const double* block) {
-  if (!h || !name || !block) return TN_ERR_INVALID;
+int ccsd_set_integrals(ccsd_handle_t h, const char* name, const double* block) try {
+  if (!h || !name || !block) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_set_integrals: bad arguments");
   int id;
   CRC(ensure_block(h, name, &id));
   CRC(tn_upload(h->tn, id, block));
   if (!strcmp(name, "PPHH")) CRC(h->A(1.0, id, "baij", 0.0, h->Vx, "abij"));   // exchange operand of getEnergy
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_set_integrals");
 }
 
-int ccsd_get_integrals(ccsd_handle_t h, const char* name, double* block) {
-  if (!h || !name || !block || !h->V.count(name)) return TN_ERR_INVALID;
+int ccsd_get_integrals(ccsd_handle_t h, const char* name, double* block) try {
+  if (!h || !name || !block || !h->V.count(name)) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_get_integrals: bad arguments");
   return tn_download(h->tn, h->V[name], block);
+} catch (...) {
+  return pt::tn_on_exception("ccsd_get_integrals");
 }
 
-int ccsd_set_vertex(ccsd_handle_t h, int nf, int np, const double* gre, const double* gim) {
-  if (!h || !gre || !gim || nf < 1 || np < h->o + h->v) return TN_ERR_INVALID;
+int ccsd_set_vertex(ccsd_handle_t h, int nf, int np, const double* gre, const double* gim) try {
+  if (!h || !gre || !gim || nf < 1 || np < h->o + h->v) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_set_vertex: bad arguments");
   const int o = h->o, v = h->v, a0 = np - v;
   // the three vertex blocks the reference slices (CoulombIntegralsFromVertex.cxx:121-136), Re and Im apart
   // (fromComplexTensor); gathered on the host: O(NF Np^2), the blocks themselves are built on the device
@@ -321,24 +336,30 @@ int ccsd_set_vertex(ccsd_handle_t h, int nf, int np, const double* gre, const do
   for (auto& pt : parts)
     for (int c = 0; c < 2; ++c) tn_free(h->tn, pt.id[c]);
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_set_vertex");
 }
 
-int ccsd_set_amplitudes(ccsd_handle_t h, const double* t1, const double* t2) {
-  if (!h) return TN_ERR_INVALID;
+int ccsd_set_amplitudes(ccsd_handle_t h, const double* t1, const double* t2) try {
+  if (!h) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_set_amplitudes: bad arguments");
   if (t1) CRC(tn_upload(h->tn, h->T1, t1));
   if (t2) { CRC(tn_upload(h->tn, h->T2, t2)); h->initial_doubles = true; }
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_set_amplitudes");
 }
 
-int ccsd_get_amplitudes(ccsd_handle_t h, double* t1, double* t2) {
-  if (!h) return TN_ERR_INVALID;
+int ccsd_get_amplitudes(ccsd_handle_t h, double* t1, double* t2) try {
+  if (!h) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_get_amplitudes: bad arguments");
   if (t1) CRC(tn_download(h->tn, h->T1, t1));
   if (t2) CRC(tn_download(h->tn, h->T2, t2));
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_get_amplitudes");
 }
 
-int ccsd_residuum(ccsd_handle_t h, int iteration, double* r1, double* r2) {
-  if (!h || !r1 || !r2) return TN_ERR_INVALID;
+int ccsd_residuum(ccsd_handle_t h, int iteration, double* r1, double* r2) try {
+  if (!h || !r1 || !r2) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_residuum: bad arguments");
   int R[2] = {-1, -1};
   int rc = alloc_pair(h, R);
   if (!rc) rc = residuum(h, iteration, h->T1, h->T2, R[0], R[1]);
@@ -346,13 +367,15 @@ int ccsd_residuum(ccsd_handle_t h, int iteration, double* r1, double* r2) {
   if (!rc) rc = tn_download(h->tn, R[1], r2);
   free_pair(h, R);
   return rc;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_residuum");
 }
 
-int ccsd_solve(ccsd_handle_t h, const CcsdOptions* opt_in, CcsdResult* res) {
-  if (!h || !res) return TN_ERR_INVALID;
+int ccsd_solve(ccsd_handle_t h, const CcsdOptions* opt_in, CcsdResult* res) try {
+  if (!h || !res) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_solve: bad arguments");
   CcsdOptions opt;
   if (opt_in) opt = *opt_in; else ccsd_default_options(&opt);
-  if (opt.mixer != CCSD_LINEAR_MIXER && opt.mixer != CCSD_DIIS_MIXER) return TN_ERR_INVALID;   // "Mixer not implemented" (:50-54)
+  if (opt.mixer != CCSD_LINEAR_MIXER && opt.mixer != CCSD_DIIS_MIXER) return pt::tn_record_error(TN_ERR_INVALID, "ccsd_solve: Mixer not implemented");   // (:50-54)
   memset(res, 0, sizeof *res);
   const int N = opt.mixer == CCSD_DIIS_MIXER ? std::max(1, opt.max_residua) : 0;
   // DIIS ring (DiisMixer.cxx:55-100): amplitudes, residua, overlap matrix bordered by -1
@@ -414,7 +437,7 @@ int ccsd_solve(ccsd_handle_t h, const CcsdOptions* opt_in, CcsdResult* res) {
       for (int r = 0; r < dim; ++r)
         for (int c = 0; c < dim; ++c) a[r * dim + c] = B[r * (N + 1) + c];
       col[0] = -1.0;
-      if (!solve_dense(a, col, dim)) { rc = TN_ERR_INVALID; break; }   // "problem diagonalization" (:37-39)
+      if (!solve_dense(a, col, dim)) { rc = pt::tn_record_error(TN_ERR_INVALID, "DiisMixer: singular B matrix"); break; }   // "problem diagonalization" (:37-39)
       for (int q = 0; q < 2 && !rc; ++q) {                             // next = sum_j w_j amplitudes_j (:161-172)
         rc = h->A(0.0, T[q], IDX[q], 0.0, T[q], IDX[q]);
         for (int j = 0; j < count && !rc; ++j) {
@@ -450,6 +473,8 @@ int ccsd_solve(ccsd_handle_t h, const CcsdOptions* opt_in, CcsdResult* res) {
   double bytes = 0;
   tn_get_stats(h->tn, &res->flops, &bytes, &res->kernel_launches);
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("ccsd_solve");
 }
 
 }  // extern "C"

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <ctime>
 #include <memory>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -34,6 +36,18 @@ int fail(int code, const char* fmt, ...) {
 // library-internal: lets the other translation units (upt.cu) report through pt_last_error()
 namespace pt {
 int record_error(int code, const char* message) { return fail(code, "%s", message); }
+// catch (...) handler of every extern "C" entry point: no C++ exception crosses the C ABI
+int on_exception(const char* where) {
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    return fail(PT_ERR_NOMEM, "%s: host memory exhausted", where);
+  } catch (const std::exception& e) {
+    return fail(PT_ERR_INVALID, "%s: %s", where, e.what());
+  } catch (...) {
+    return fail(PT_ERR_INVALID, "%s: unknown C++ exception", where);
+  }
+}
 }  // namespace pt
 
 namespace {
@@ -162,6 +176,7 @@ struct Triple { int i, j, k; };
 // reference enumeration order, CcsdPerturbativeTriples.cxx:156-158
 void enumerate_triples(int o, std::vector<Triple>& out) {
   out.clear();
+  out.reserve((size_t)o * (o + 1) / 2 * (o + 2) / 3);   // an absurd o fails here, at once (std::length_error / bad_alloc)
   for (int i = 0; i < o; ++i)
     for (int j = i; j < o; ++j)
       for (int k = j; k < o; ++k) out.push_back({i, j, k});
@@ -363,7 +378,7 @@ const char* pt_version(void) { return "sisi4s_b200 (T) 0.2 sm_100a"; }
 
 int64_t pt_num_triples(int o) { return (int64_t)o * (o + 1) * (o + 2) / 6; }
 
-int pt_partition(int o, int nranks, int rank, int64_t* begin, int64_t* end) {
+int pt_partition(int o, int nranks, int rank, int64_t* begin, int64_t* end) try {
   if (o < 1 || nranks < 1 || rank < 0 || rank >= nranks || !begin || !end)
     return fail(PT_ERR_INVALID, "pt_partition: bad arguments");
   std::vector<Triple> tr;
@@ -385,6 +400,8 @@ int pt_partition(int o, int nranks, int rank, int64_t* begin, int64_t* end) {
   *begin = cut(rank);
   *end = cut(rank + 1);
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_partition");
 }
 
 int64_t pt_estimate_device_bytes(int o, int v, int slab_slots, int hole_block) {
@@ -404,7 +421,7 @@ int64_t pt_estimate_device_bytes(int o, int v, int slab_slots, int hole_block) {
 }
 
 int pt_plan_hole_blocks(int o, int hole_block, int64_t begin, int64_t end, int64_t* n_groups, int32_t* max_active_holes,
-                        int64_t* slab_loads) {
+                        int64_t* slab_loads) try {
   if (o < 1 || hole_block < 1 || begin < 0 || begin > end || end > pt_num_triples(o))
     return fail(PT_ERR_INVALID, "pt_plan_hole_blocks: bad arguments");
   std::vector<Triple> tr;
@@ -451,11 +468,13 @@ int pt_plan_hole_blocks(int o, int hole_block, int64_t begin, int64_t end, int64
   if (max_active_holes) *max_active_holes = max_active;
   if (slab_loads) *slab_loads = loads;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_plan_hole_blocks");
 }
 
 int pt_create(pt_handle_t* out, int o, int v, int device) { return pt_create_ex(out, o, o, v, device); }
 
-int pt_create_ex(pt_handle_t* out, int o, int o_all, int v, int device) {
+int pt_create_ex(pt_handle_t* out, int o, int o_all, int v, int device) try {
   if (!out || o < 1 || v < 1 || o_all < o) return fail(PT_ERR_INVALID, "pt_create: need 1 <= o_act <= o_all, v >= 1");
   if ((v + TILE - 1) / TILE > 255) return fail(PT_ERR_UNSUPPORTED, "pt_create: v too large (%d particle ranges > 255)", (v + TILE - 1) / TILE);
   int ndev = 0;
@@ -475,9 +494,11 @@ int pt_create_ex(pt_handle_t* out, int o, int o_all, int v, int device) {
   RC(init_handle(h.get(), o, o_all, v, device, prop.multiProcessorCount));
   *out = h.release();
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_create_ex");
 }
 
-int pt_destroy(pt_handle_t h) {
+int pt_destroy(pt_handle_t h) try {
   if (!h) return PT_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -497,9 +518,11 @@ int pt_destroy(pt_handle_t h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_destroy");
 }
 
-int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
+int pt_set_option(pt_handle_t h, const char* key, int64_t value) try {
   if (!h || !key) return fail(PT_ERR_INVALID, "pt_set_option: null");
   const bool any_input = h->have_eps || h->have_t1 || h->have_t2 || h->have_pphh || h->have_hhhp || h->Vt || h->gp;
   if (!strcmp(key, "engine")) {
@@ -552,17 +575,21 @@ int pt_set_option(pt_handle_t h, const char* key, int64_t value) {
     return fail(PT_ERR_INVALID, "pt_set_option: unknown key '%s'", key);
   }
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_option");
 }
 
-int pt_sync(pt_handle_t h) {
+int pt_sync(pt_handle_t h) try {
   if (!h) return fail(PT_ERR_INVALID, "pt_sync: null");
   CU(cudaSetDevice(h->device));
   RC(sync_uploads(h));
   CU(cudaStreamSynchronize(h->stream));
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_sync");
 }
 
-int pt_set_eigenenergies(pt_handle_t h, const double* epsi, const double* epsa) {
+int pt_set_eigenenergies(pt_handle_t h, const double* epsi, const double* epsa) try {
   if (!h || !epsi || !epsa) return fail(PT_ERR_INVALID, "pt_set_eigenenergies: null");
   CU(cudaSetDevice(h->device));
   UploadScope up(h);
@@ -574,9 +601,11 @@ int pt_set_eigenenergies(pt_handle_t h, const double* epsi, const double* epsa) 
   RC(up.done());
   h->have_eps = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_eigenenergies");
 }
 
-int pt_set_singles(pt_handle_t h, const double* t1) {
+int pt_set_singles(pt_handle_t h, const double* t1) try {
   if (!h || !t1) return fail(PT_ERR_INVALID, "pt_set_singles: null");
   CU(cudaSetDevice(h->device));
   UploadScope up(h);
@@ -587,9 +616,11 @@ int pt_set_singles(pt_handle_t h, const double* t1) {
   RC(up.done());
   h->have_t1 = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_singles");
 }
 
-int pt_set_pphh(pt_handle_t h, const double* vabij) {
+int pt_set_pphh(pt_handle_t h, const double* vabij) try {
   if (!h || !vabij) return fail(PT_ERR_INVALID, "pt_set_pphh: null");
   CU(cudaSetDevice(h->device));
   UploadScope up(h);
@@ -609,9 +640,11 @@ int pt_set_pphh(pt_handle_t h, const double* vabij) {
   RC(up.done());
   h->have_pphh = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_pphh");
 }
 
-int pt_set_singles_pair(pt_handle_t h, const double* t1b, const double* vabij_b) {
+int pt_set_singles_pair(pt_handle_t h, const double* t1b, const double* vabij_b) try {
   if (!h || !t1b || !vabij_b) return fail(PT_ERR_INVALID, "pt_set_singles_pair: null");
   if (h->hole_block) return fail(PT_ERR_UNSUPPORTED, "pt_set_singles_pair: not in hole_block mode");
   CU(cudaSetDevice(h->device));
@@ -626,9 +659,11 @@ int pt_set_singles_pair(pt_handle_t h, const double* t1b, const double* vabij_b)
   h->stats.kernel_launches += 1;
   RC(up.done());
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_singles_pair");
 }
 
-int pt_set_doubles(pt_handle_t h, const double* t2) {
+int pt_set_doubles(pt_handle_t h, const double* t2) try {
   if (!h || !t2) return fail(PT_ERR_INVALID, "pt_set_doubles: null");
   CU(cudaSetDevice(h->device));
   UploadScope up(h);
@@ -661,9 +696,11 @@ int pt_set_doubles(pt_handle_t h, const double* t2) {
   RC(up.done());
   h->have_t2 = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_doubles");
 }
 
-int pt_set_doubles_hole(pt_handle_t h, const double* t2_xl) {
+int pt_set_doubles_hole(pt_handle_t h, const double* t2_xl) try {
   if (!h || !t2_xl) return fail(PT_ERR_INVALID, "pt_set_doubles_hole: null");
   if (h->hole_block) return fail(PT_ERR_INVALID, "pt_set_doubles_hole: not used in hole_block mode (pt_set_doubles takes the full tensor)");
   CU(cudaSetDevice(h->device));
@@ -678,9 +715,11 @@ int pt_set_doubles_hole(pt_handle_t h, const double* t2_xl) {
   RC(up.done());
   h->have_t2h = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_doubles_hole");
 }
 
-int pt_set_hhhp(pt_handle_t h, const double* vijka) {
+int pt_set_hhhp(pt_handle_t h, const double* vijka) try {
   if (!h || !vijka) return fail(PT_ERR_INVALID, "pt_set_hhhp: null");
   CU(cudaSetDevice(h->device));
   UploadScope up(h);
@@ -707,6 +746,8 @@ int pt_set_hhhp(pt_handle_t h, const double* vijka) {
   RC(up.done());
   h->have_hhhp = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_hhhp");
 }
 
 static int ensure_ppph_buffers(pt_handle_t h, bool need_stage) {
@@ -738,7 +779,7 @@ static int pack_into_slot(pt_handle_t h, const double* src, int k, int slot) {
   return PT_OK;
 }
 
-int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
+int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) try {
   if (!h || !slabs) return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: null");
   if (k0 < 0 || k1 > h->oh() || k0 >= k1) return fail(PT_ERR_INVALID, "pt_set_ppph_slabs: range [%d,%d) of %d", k0, k1, h->oh());
   if (h->blocked())
@@ -757,9 +798,11 @@ int pt_set_ppph_slabs(pt_handle_t h, int k0, int k1, const double* slabs) {
   }
   RC(up.done());
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_ppph_slabs");
 }
 
-int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
+int pt_set_ppph_host(pt_handle_t h, const double* vabci) try {
   if (!h || !vabci) return fail(PT_ERR_INVALID, "pt_set_ppph_host: null");
   if (!h->blocked() && !(h->async_upload && !h->keep_raw && !h->hole_block)) return pt_set_ppph_slabs(h, 0, h->oh(), vabci);
   CU(cudaSetDevice(h->device));
@@ -772,9 +815,11 @@ int pt_set_ppph_host(pt_handle_t h, const double* vabci) {
   std::fill(h->slot_of.begin(), h->slot_of.end(), -1);
   std::fill(h->hole_in.begin(), h->hole_in.end(), -1);
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_ppph_host");
 }
 
-int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double* gim) {
+int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double* gim) try {
   if (!h || !gre || !gim) return fail(PT_ERR_INVALID, "pt_set_vertex: null");
   if (nf < 1 || np < h->oh() + h->d.v) return fail(PT_ERR_INVALID, "pt_set_vertex: nf=%d np=%d (o+v=%d)", nf, np, h->oh() + h->d.v);
   if (h->d.vd != h->d.v) return fail(PT_ERR_UNSUPPORTED, "pt_set_vertex: not with a stacked particle contraction");
@@ -817,9 +862,11 @@ int pt_set_vertex(pt_handle_t h, int nf, int np, const double* gre, const double
   }
   RC(up.done());
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_set_vertex");
 }
 
-int pt_use_vertex_integrals(pt_handle_t h) {
+int pt_use_vertex_integrals(pt_handle_t h) try {
   if (!h) return fail(PT_ERR_INVALID, "pt_use_vertex_integrals: null");
   if (!h->gp) return fail(PT_ERR_MISSING, "Missing argument: CoulombVertex (pt_set_vertex before pt_use_vertex_integrals)");
   if (!h->hole_block && h->d.o != h->d.ol)
@@ -853,9 +900,11 @@ int pt_use_vertex_integrals(pt_handle_t h) {
   RC(up.done());
   h->have_pphh = h->have_hhhp = true;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_use_vertex_integrals");
 }
 
-int pt_vertex_integrals(pt_handle_t h, const char* block, double* out) {
+int pt_vertex_integrals(pt_handle_t h, const char* block, double* out) try {
   if (!h || !block || !out) return fail(PT_ERR_INVALID, "pt_vertex_integrals: null");
   if (!h->gp) return fail(PT_ERR_MISSING, "Missing argument: CoulombVertex");
   if (!h->hole_block && h->d.o != h->d.ol)
@@ -891,6 +940,8 @@ int pt_vertex_integrals(pt_handle_t h, const char* block, double* out) {
   }
   CU(cudaStreamSynchronize(h->stream));
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_vertex_integrals");
 }
 
 // blocked mode: make the slabs of all holes in `need` resident (LRU replacement among the slots
@@ -1047,7 +1098,7 @@ static int run_naive(pt_handle_t h, const std::vector<Triple>& tr, std::vector<d
 // the triples `tr` (any order) -> e[n]; shared by pt_run and pt_run_list
 static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_triples, double* e_per_triple);
 
-int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double* e_per_triple) {
+int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double* e_per_triple) try {
   if (!h || !e_triples) return fail(PT_ERR_INVALID, "pt_run: null");
   CU(cudaSetDevice(h->device));
   RC(check_inputs(h));
@@ -1057,9 +1108,11 @@ int pt_run(pt_handle_t h, int64_t begin, int64_t end, double* e_triples, double*
     return fail(PT_ERR_INVALID, "pt_run: triple range [%lld,%lld) of %zu", (long long)begin, (long long)end, all.size());
   std::vector<Triple> tr(all.begin() + begin, all.begin() + end);
   return run_triples(h, tr, e_triples, e_per_triple);
+} catch (...) {
+  return pt::on_exception("pt_run");
 }
 
-int pt_run_list(pt_handle_t h, int64_t n, const int64_t* triples, double* e_triples, double* e_per_triple) {
+int pt_run_list(pt_handle_t h, int64_t n, const int64_t* triples, double* e_triples, double* e_per_triple) try {
   if (!h || !e_triples || n < 0 || (n > 0 && !triples)) return fail(PT_ERR_INVALID, "pt_run_list: null");
   CU(cudaSetDevice(h->device));
   RC(check_inputs(h));
@@ -1072,6 +1125,8 @@ int pt_run_list(pt_handle_t h, int64_t n, const int64_t* triples, double* e_trip
     tr[(size_t)m] = all[(size_t)triples[m]];
   }
   return run_triples(h, tr, e_triples, e_per_triple);
+} catch (...) {
+  return pt::on_exception("pt_run_list");
 }
 
 static double wall_now() {
@@ -1321,14 +1376,16 @@ static int run_triples(pt_handle_t h, const std::vector<Triple>& tr, double* e_t
   return PT_OK;
 }
 
-int pt_get_stats(pt_handle_t h, PtStats* s) {
+int pt_get_stats(pt_handle_t h, PtStats* s) try {
   if (!h || !s) return fail(PT_ERR_INVALID, "pt_get_stats: null");
   h->stats.device_bytes = h->bytes_alloc;
   *s = h->stats;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_get_stats");
 }
 
-int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, double* out) {
+int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, double* out) try {
   if (!h || !out) return fail(PT_ERR_INVALID, "pt_debug_w_tile: null");
   if (h->hole_block || h->blocked()) return fail(PT_ERR_UNSUPPORTED, "pt_debug_w_tile: all-resident engines only");
   CU(cudaSetDevice(h->device));
@@ -1346,9 +1403,11 @@ int pt_debug_w_tile(pt_handle_t h, int x, int y, int z, int ra, int rb, int rc, 
   CU(cudaMemcpyAsync(out, d_out, XT_DBL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_debug_w_tile");
 }
 
-int pt_bench_vertex_gemm(pt_handle_t h, int what, int reps, double* seconds, double* flop) {
+int pt_bench_vertex_gemm(pt_handle_t h, int what, int reps, double* seconds, double* flop) try {
   if (!h || !seconds || !flop || reps < 1) return fail(PT_ERR_INVALID, "pt_bench_vertex_gemm: args");
   if (!h->gp || !h->Vt) return fail(PT_ERR_MISSING, "Missing argument: CoulombVertex");
   CU(cudaSetDevice(h->device));
@@ -1371,9 +1430,11 @@ int pt_bench_vertex_gemm(pt_handle_t h, int what, int reps, double* seconds, dou
   *seconds = ms * 1e-3 / reps;
   *flop = what == 0 ? 2.0 * k2 * v * v * v : 2.0 * k2 * v * v * o * o;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_bench_vertex_gemm");
 }
 
-int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double* tflops, double* sm_mhz_est) {
+int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double* tflops, double* sm_mhz_est) try {
   if (!h || !tflops) return fail(PT_ERR_INVALID, "pt_bench_fp64: null");
   if (warps_per_sm < 1 || warps_per_sm > 32 || iters < 1) return fail(PT_ERR_INVALID, "pt_bench_fp64: args");
   CU(cudaSetDevice(h->device));
@@ -1403,6 +1464,8 @@ int pt_bench_fp64(pt_handle_t h, int mode, int warps_per_sm, int iters, double* 
   *tflops = flops / sec * 1e-12;
   if (sm_mhz_est) *sm_mhz_est = (double)mx / sec * 1e-6;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_bench_fp64");
 }
 
 }  // extern "C"

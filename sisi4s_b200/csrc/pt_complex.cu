@@ -19,7 +19,14 @@
 #include "../../include/sisi4s_pt.h"
 #include "../../include/sisi4s_tn.h"
 
+namespace pt {
+int record_error(int code, const char* message);
+int on_exception(const char* where);   // pt_api.cu: what pt_last_error() returns
+}
+
 namespace {
+
+int tn_failed() { return pt::record_error(PT_ERR_CUDA, tn_last_error()); }
 
 struct Guard {
   pt_handle_t pt = nullptr;
@@ -57,25 +64,25 @@ extern "C" int pt_complex_triples(int o, int v, int device, const double* epsi, 
                                   const double* t1_im, const double* t2_re, const double* t2_im, const double* pphh_re,
                                   const double* pphh_im, const double* phhh_re, const double* phhh_im, int nf, int np,
                                   const double* gamma_re, const double* gamma_im, double* e_triples,
-                                  double* e_per_triple) {
+                                  double* e_per_triple) try {
   if (o < 1 || v < 1 || nf < 1 || np < o + v || !epsi || !epsa || !t1_re || !t1_im || !t2_re || !t2_im || !pphh_re ||
       !pphh_im || !phhh_re || !phhh_im || !gamma_re || !gamma_im || !e_triples)
-    return PT_ERR_INVALID;
+    return pt::record_error(PT_ERR_INVALID, "pt_complex_triples: bad arguments (need o, v, nf >= 1, np >= o + v, non-null arrays)");
   Guard g;
   const int a0 = np - v;
   const size_t vv = (size_t)v * v, n4 = vv * v * o;
   // ---- complex PPPH block V[b,c,d,k] = sum_F conj(G[F,d,b]) G[F,c,k] on the device (:341-348)
   std::vector<double> vr(n4), vi(n4);
   {
-    if (tn_create(&g.tn, device)) return PT_ERR_CUDA;
+    if (tn_create(&g.tn, device)) return tn_failed();
     auto block = [&](const double* src, int p0, int npart, int q0, int nq, int* id) -> int {   // G[:, p0:p0+npart, q0:q0+nq]
       std::vector<double> buf((size_t)nf * npart * nq);
       for (int q = 0; q < nq; ++q)
         for (int p = 0; p < npart; ++p)
           memcpy(&buf[(size_t)nf * (p + (size_t)npart * q)], src + (size_t)nf * ((p0 + p) + (size_t)np * (q0 + q)), sizeof(double) * nf);
       const int64_t lens[3] = {nf, npart, nq};
-      if (tn_tensor(g.tn, 3, lens, id)) return PT_ERR_CUDA;
-      return tn_upload(g.tn, *id, buf.data()) ? PT_ERR_CUDA : PT_OK;
+      if (tn_tensor(g.tn, 3, lens, id)) return tn_failed();
+      return tn_upload(g.tn, *id, buf.data()) ? tn_failed() : PT_OK;
     };
     int abr, abi, air, aii, tr, ti;
     PRC(block(gamma_re, a0, v, a0, v, &abr));
@@ -83,14 +90,14 @@ extern "C" int pt_complex_triples(int o, int v, int device, const double* epsi, 
     PRC(block(gamma_re, a0, v, 0, o, &air));
     PRC(block(gamma_im, a0, v, 0, o, &aii));
     const int64_t l4[4] = {v, v, v, o};
-    if (tn_tensor(g.tn, 4, l4, &tr) || tn_tensor(g.tn, 4, l4, &ti)) return PT_ERR_CUDA;
+    if (tn_tensor(g.tn, 4, l4, &tr) || tn_tensor(g.tn, 4, l4, &ti)) return tn_failed();
     int rc = tn_contract(g.tn, 1.0, abr, "Fdb", air, "Fck", 0.0, tr, "bcdk");      // Re: ab_r ai_r + ab_i ai_i
     if (!rc) rc = tn_contract(g.tn, 1.0, abi, "Fdb", aii, "Fck", 1.0, tr, "bcdk");
     if (!rc) rc = tn_contract(g.tn, 1.0, abr, "Fdb", aii, "Fck", 0.0, ti, "bcdk"); // Im: ab_r ai_i - ab_i ai_r
     if (!rc) rc = tn_contract(g.tn, -1.0, abi, "Fdb", air, "Fck", 1.0, ti, "bcdk");
     if (!rc) rc = tn_download(g.tn, tr, vr.data());
     if (!rc) rc = tn_download(g.tn, ti, vi.data());
-    if (rc) return PT_ERR_CUDA;
+    if (rc) return tn_failed();
     tn_destroy(g.tn);
     g.tn = nullptr;
   }
@@ -148,4 +155,6 @@ extern "C" int pt_complex_triples(int o, int v, int device, const double* epsi, 
   *e_triples = total;
   if (e_per_triple) memcpy(e_per_triple, per.data(), sizeof(double) * (size_t)ntr);
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_complex_triples");
 }

@@ -18,6 +18,8 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -38,6 +40,26 @@ int tn_fail(int code, const char* fmt, ...) {
   g_tn_error = buf;
   return code;
 }
+}  // namespace
+
+namespace pt {
+// library-internal (ccsd_solver.cu): messages for tn_last_error(), and the catch (...) handler of the entry points
+int tn_record_error(int code, const char* message) { return tn_fail(code, "%s", message); }
+int tn_on_exception(const char* where) {
+  try {
+    throw;
+  } catch (const std::bad_alloc&) {
+    return tn_fail(TN_ERR_NOMEM, "%s: host memory exhausted", where);
+  } catch (const std::exception& e) {
+    return tn_fail(TN_ERR_INVALID, "%s: %s", where, e.what());
+  } catch (...) {
+    return tn_fail(TN_ERR_INVALID, "%s: unknown C++ exception", where);
+  }
+}
+}  // namespace pt
+
+namespace {
+
 #define TCU(call)                                                                                          \
   do {                                                                                                     \
     cudaError_t e_ = (call);                                                                               \
@@ -242,7 +264,7 @@ extern "C" {
 
 const char* tn_last_error(void) { return g_tn_error.c_str(); }
 
-int tn_create(tn_handle_t* out, int device) {
+int tn_create(tn_handle_t* out, int device) try {
   if (!out) return tn_fail(TN_ERR_INVALID, "tn_create: null");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -261,9 +283,11 @@ int tn_create(tn_handle_t* out, int device) {
   }
   *out = h;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_create");
 }
 
-int tn_destroy(tn_handle_t h) {
+int tn_destroy(tn_handle_t h) try {
   if (!h) return TN_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -274,9 +298,11 @@ int tn_destroy(tn_handle_t h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_destroy");
 }
 
-int tn_tensor(tn_handle_t h, int ndim, const int64_t* lens, int* id) {
+int tn_tensor(tn_handle_t h, int ndim, const int64_t* lens, int* id) try {
   if (!h || !id || ndim < 0 || ndim > TN_MAXD || (ndim > 0 && !lens)) return tn_fail(TN_ERR_INVALID, "tn_tensor: arguments");
   TCU(cudaSetDevice(h->device));
   TnTensor t;
@@ -296,9 +322,11 @@ int tn_tensor(tn_handle_t h, int ndim, const int64_t* lens, int* id) {
   h->t.push_back(t);
   *id = (int)h->t.size() - 1;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_tensor");
 }
 
-int tn_free(tn_handle_t h, int id) {
+int tn_free(tn_handle_t h, int id) try {
   TnTensor* t;
   TRC(get(h, id, &t));
   TCU(cudaSetDevice(h->device));
@@ -306,9 +334,11 @@ int tn_free(tn_handle_t h, int id) {
   TCU(cudaFree(t->d));
   *t = TnTensor();
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_free");
 }
 
-int tn_upload(tn_handle_t h, int id, const double* host) {
+int tn_upload(tn_handle_t h, int id, const double* host) try {
   TnTensor* t;
   TRC(get(h, id, &t));
   if (!host) return tn_fail(TN_ERR_INVALID, "tn_upload: null");
@@ -316,9 +346,11 @@ int tn_upload(tn_handle_t h, int id, const double* host) {
   TCU(cudaMemcpyAsync(t->d, host, (size_t)t->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   TCU(cudaStreamSynchronize(h->stream));
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_upload");
 }
 
-int tn_download(tn_handle_t h, int id, double* host) {
+int tn_download(tn_handle_t h, int id, double* host) try {
   TnTensor* t;
   TRC(get(h, id, &t));
   if (!host) return tn_fail(TN_ERR_INVALID, "tn_download: null");
@@ -326,9 +358,11 @@ int tn_download(tn_handle_t h, int id, double* host) {
   TCU(cudaMemcpyAsync(host, t->d, (size_t)t->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   TCU(cudaStreamSynchronize(h->stream));
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_download");
 }
 
-int tn_add(tn_handle_t h, double alpha, int a, const char* ia, double beta, int c, const char* ic) {
+int tn_add(tn_handle_t h, double alpha, int a, const char* ia, double beta, int c, const char* ic) try {
   TnTensor *A, *C;
   TRC(get(h, a, &A));
   TRC(get(h, c, &C));
@@ -346,10 +380,12 @@ int tn_add(tn_handle_t h, double alpha, int a, const char* ia, double beta, int 
   h->launches += 1;
   h->bytes += 8.0 * (double)A->n * (beta == 0.0 ? 2.0 : 3.0);
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_add");
 }
 
 int tn_contract(tn_handle_t h, double alpha, int a, const char* ia, int b, const char* ib, double beta, int c,
-                const char* ic) {
+                const char* ic) try {
   TnTensor *A, *B, *C;
   TRC(get(h, a, &A));
   TRC(get(h, b, &B));
@@ -443,9 +479,11 @@ int tn_contract(tn_handle_t h, double alpha, int a, const char* ia, int b, const
     h->bytes += 8.0 * (double)(M * N) * 3.0;
   }
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_contract");
 }
 
-int tn_dot(tn_handle_t h, int a, int b, double* out) {
+int tn_dot(tn_handle_t h, int a, int b, double* out) try {
   TnTensor *A, *B;
   TRC(get(h, a, &A));
   TRC(get(h, b, &B));
@@ -458,9 +496,11 @@ int tn_dot(tn_handle_t h, int a, int b, double* out) {
   TCU(cudaMemcpyAsync(out, h->dot + DOT_BLOCKS, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   TCU(cudaStreamSynchronize(h->stream));
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_dot");
 }
 
-int tn_excitation_divide(tn_handle_t h, int r, int t, int epsi, int epsa, double shift) {
+int tn_excitation_divide(tn_handle_t h, int r, int t, int epsi, int epsa, double shift) try {
   TnTensor *R, *T, *Ei, *Ea;
   TRC(get(h, r, &R));
   TRC(get(h, t, &T));
@@ -478,14 +518,18 @@ int tn_excitation_divide(tn_handle_t h, int r, int t, int epsi, int epsa, double
   TCU(cudaGetLastError());
   h->launches += 1;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_excitation_divide");
 }
 
-int tn_get_stats(tn_handle_t h, double* flops, double* bytes, int64_t* launches) {
+int tn_get_stats(tn_handle_t h, double* flops, double* bytes, int64_t* launches) try {
   if (!h) return tn_fail(TN_ERR_INVALID, "tn_get_stats: null");
   if (flops) *flops = h->flops;
   if (bytes) *bytes = h->bytes;
   if (launches) *launches = h->launches;
   return TN_OK;
+} catch (...) {
+  return pt::tn_on_exception("tn_get_stats");
 }
 
 }  // extern "C"

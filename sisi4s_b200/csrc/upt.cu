@@ -10,12 +10,13 @@
 #include "../../include/sisi4s_tn.h"
 
 namespace pt {
-int record_error(int code, const char* message);   // pt_api.cu
+int record_error(int code, const char* message);
+int on_exception(const char* where);   // pt_api.cu
 }
 
 extern "C" int pt_spin_orbital_triples(int o, int v, int device, const double* epsi, const double* epsa, const double* tai,
                                        const double* tabij, const double* vabij, const double* vijka,
-                                       const double* vabci, double* e_triples) {
+                                       const double* vabci, double* e_triples) try {
   if (o < 1 || v < 1 || !epsi || !epsa || !tai || !tabij || !vabij || !vijka || !vabci || !e_triples)
     return pt::record_error(PT_ERR_INVALID, "pt_spin_orbital_triples: bad arguments");
   tn_handle_t tn = nullptr;
@@ -61,4 +62,6 @@ extern "C" int pt_spin_orbital_triples(int o, int v, int device, const double* e
   if (rc) return pt::record_error(PT_ERR_CUDA, tn_last_error());
   *e_triples = dot / 36.0;
   return PT_OK;
+} catch (...) {
+  return pt::on_exception("pt_spin_orbital_triples");
 }

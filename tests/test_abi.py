@@ -84,6 +84,9 @@ def test_host_only_entry_points():
     b, e = C.c_int64(), C.c_int64()
     assert lib.pt_partition(5, 2, 2, C.byref(b), C.byref(e)) == -1
     assert b"pt_partition" in lib.pt_last_error()
+    # no C++ exception crosses the C ABI: an enumeration that cannot be allocated is an error code + message
+    assert lib.pt_partition(1 << 21, 2, 0, C.byref(b), C.byref(e)) in (-1, -4)
+    assert b"pt_partition" in lib.pt_last_error()
 
 
 def test_partition_is_weight_balanced():
