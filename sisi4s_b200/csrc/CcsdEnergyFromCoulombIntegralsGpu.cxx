@@ -8,8 +8,8 @@
 // converged amplitudes are written back into CTF tensors by rank 0 (Tensor::write is collective: the other
 // ranks contribute zero elements).
 //
-// Written against the reference headers; syntax-checked in tests/test_abi.py (no MPI / CTF in this repository's
-// container), see INTEGRATION.md.
+// Written against the reference headers; run in tests/test_plugin_harness.py (one rank, stand-ins for MPI / CTF),
+// see INTEGRATION.md section 4.
 #include "CcsdEnergyFromCoulombIntegralsGpu.hpp"
 
 #include <Sisi4s.hpp>

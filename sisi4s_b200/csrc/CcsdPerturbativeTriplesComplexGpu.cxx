@@ -5,7 +5,7 @@
 // its instantiations: real amplitudes / integrals (the imaginary parts are then zero) and complex ones.
 // The tensors are gathered once with Tensor::read_all, split into real and imaginary parts
 // (fromComplexTensor) and handed to the C ABI; rank 0's GPU does the work and the scalar is broadcast.
-// Written against the reference headers; syntax-checked in tests/test_abi.py, see INTEGRATION.md.
+// Written against the reference headers; run in tests/test_plugin_harness.py, see INTEGRATION.md section 4.
 #include "CcsdPerturbativeTriplesComplexGpu.hpp"
 
 #include <Sisi4s.hpp>

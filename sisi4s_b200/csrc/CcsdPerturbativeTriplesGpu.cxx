@@ -8,8 +8,8 @@
 // the C ABI (include/sisi4s_pt.h) and runs its share of the i<=j<=k triples on its GPU.
 // The only communication on the path is one ncclAllReduce of the scalar energy.
 //
-// Written against the reference headers; it cannot be linked in the build container of this
-// repository (no MPI / Cyclops CTF there), see INTEGRATION.md for how it is compile-checked.
+// Written against the reference headers.  The sisi4s executable cannot be built in this repository's
+// container (no MPI / Cyclops CTF there); INTEGRATION.md section 4 says how the class is run and checked anyway.
 #include "CcsdPerturbativeTriplesGpu.hpp"
 
 #include <DryTensor.hpp>

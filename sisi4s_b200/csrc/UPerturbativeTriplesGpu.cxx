@@ -3,7 +3,7 @@
 // Replaces UPerturbativeTriples::run (reference src/algorithms/UPerturbativeTriples.cxx:19-305).  The seven
 // tensors are gathered once with Tensor::read_all and handed to the C ABI; rank 0's GPU evaluates the
 // statements on the device tensor engine (csrc/upt.cu) and the scalar is broadcast.
-// Written against the reference headers; syntax-checked in tests/test_abi.py, see INTEGRATION.md.
+// Written against the reference headers; run in tests/test_plugin_harness.py, see INTEGRATION.md section 4.
 #include "UPerturbativeTriplesGpu.hpp"
 
 #include <Sisi4s.hpp>
