@@ -6,6 +6,14 @@
 // (reference src/algorithms/UPerturbativeTriples.cxx:19-27,305); registered under a new name because
 // AlgorithmFactory silently overwrites duplicate registrations (src/algorithms/Algorithm.hpp:158-160).
 
+//
+// Plan arguments (all real tensors, spin-orbital, antisymmetrised where the reference expects it):
+//   HoleEigenEnergies[o], ParticleEigenEnergies[v], CcsdSinglesAmplitudes[v,o], CcsdDoublesAmplitudes[v,v,o,o],
+//   PPHHCoulombIntegrals[v,v,o,o], HHHPCoulombIntegrals[o,o,o,v], PPPHCoulombIntegrals[v,v,v,o];
+//   device (integer, optional, default 0): the GPU rank 0 evaluates the statements on.
+// Output: PerturbativeTriplesEnergy = the triples energy alone.
+// Memory: three v^3 o^3 FP64 tensors on the device (the reference holds the same three in CTF).
+
 #include <algorithms/Algorithm.hpp>
 
 namespace sisi4s {
