@@ -216,3 +216,40 @@ def test_hole_block_walk_plan_on_the_host():
             parts += plan(o, b, lo.value, hi.value)[0]
         assert g <= parts <= g + 3 * nb * nb
     assert lib.pt_plan_hole_blocks(5, 0, 0, 1, None, None, None) == -1
+
+
+def test_partition_and_hole_block_plan_properties():
+    """Property test of the two host-side planners over random shapes (hypothesis): pt_partition tiles the
+    enumeration with ranks within one triple's weight of the mean; pt_plan_hole_blocks of any sub-range keeps at most
+    min(3b, o) holes active, needs at least the distinct holes it touches and at most groups * 3b slab loads."""
+    from hypothesis import given, settings, strategies as st
+    _ensure_built()
+    lib = _lib.load()
+
+    @settings(max_examples=60, deadline=None)
+    @given(o=st.integers(1, 24), n=st.integers(1, 12), b=st.integers(1, 9), cut=st.tuples(st.floats(0, 1), st.floats(0, 1)))
+    def check(o, n, b, cut):
+        tr = [(i, j, k) for i in range(o) for j in range(i, o) for k in range(j, o)]
+        w = [[6, 3, 3, 1][(i == j) + 2 * (j == k)] for (i, j, k) in tr]
+        prev, loads = 0, []
+        for r in range(n):
+            lo, hi = C.c_int64(), C.c_int64()
+            assert lib.pt_partition(o, n, r, C.byref(lo), C.byref(hi)) == 0
+            assert lo.value == prev <= hi.value
+            prev = hi.value
+            loads.append(sum(w[lo.value:hi.value]))
+        assert prev == len(tr) and sum(loads) == sum(w)
+        assert max(loads) <= sum(w) / n + 6
+        lo, hi = sorted(int(c * len(tr)) for c in cut)
+        g, a, s = C.c_int64(), C.c_int32(), C.c_int64()
+        assert lib.pt_plan_hole_blocks(o, b, lo, hi, C.byref(g), C.byref(a), C.byref(s)) == 0
+        work = [t for t in tr[lo:hi] if not (t[0] == t[1] == t[2])]
+        touched = {h for t in work for h in t}
+        bw = min(b, o)
+        keys = {(t[0] // bw, t[1] // bw, t[2] // bw) for t in work}
+        assert g.value == len(keys)
+        assert a.value <= min(3 * b, o)
+        assert len(touched) <= s.value <= max(1, g.value) * min(3 * b, o)
+        assert (g.value == 0) == (not work)
+
+    check()
